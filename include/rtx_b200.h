@@ -1,0 +1,196 @@
+/*
+ * rtx_b200.h -- C ABI of the B200-native closest-hit path.
+ * Library: opencl_raytracer_b200/lib/librtx_b200.so (CUDA runtime linked
+ * statically; sm_100a only; no CPU fallback -- every entry point that needs a
+ * device fails with RTX_ERR_NO_DEVICE / RTX_ERR_CUDA when there is none).
+ *
+ * Drop-in boundary: the reference's device host layer, include/opencl_host.h
+ * :127-131 / src/opencl_host.cc, as called by src/render.cc:82-117.
+ *
+ *   reference (C++)                                          this ABI
+ *   -------------------------------------------------------  -------------------
+ *   static void OpenCLHost::printInfo()   opencl_host.cc:76  rtx_print_info, rtx_device_info
+ *   OpenCLHost::OpenCLHost(const RayTracer&)  .cc:15-75      rtx_create
+ *   void upload(faces,nodes,aabbs,vertices,vnormals) :120    rtx_upload
+ *   bool operator()()                         .cc:137-149    rtx_render
+ *   void download(float *image)               .cc:150-153    rtx_download
+ *   ~OpenCLHost (implicit)                                   rtx_destroy
+ *   check()/getErrorString  opencl_host.h:21-126             return codes + rtx_last_error
+ *
+ * The C++ adapter that restores the reference's class (and its print-and-exit
+ * error behaviour) on top of this ABI is opencl_raytracer_b200/shadow/
+ * opencl_host.h; INTEGRATION.md shows the build line.
+ *
+ * Conventions: plain pointers and sizes; all vector arrays use the
+ * reference's 16-byte Vec3f stride (include/vec3.h:93-94) and the pad lane is
+ * ignored (defined as 0); every call is blocking unless its name ends in
+ * _async; nothing throws; 0 = success.  One context = one CUDA device.  A
+ * context is not thread-safe; different contexts are independent.
+ */
+#ifndef RTX_B200_H
+#define RTX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTX_OK               0
+#define RTX_ERR_ARG          1  /* null pointer, inconsistent sizes, malformed BVH arrays */
+#define RTX_ERR_NO_DEVICE    2  /* "No device found" (opencl_host.cc:30-31) */
+#define RTX_ERR_CUDA         3  /* a CUDA runtime call failed; see rtx_last_error */
+#define RTX_ERR_UNSUPPORTED  4  /* option outside this path (ambient occlusion) */
+#define RTX_ERR_STATE        5  /* call order: render before upload, ... */
+#define RTX_ERR_NOMEM        6
+
+#define RTX_NO_HIT 0xffffffffu
+
+typedef struct rtx_ctx rtx_ctx;
+
+/* Mirrors RayTracer::Options + totalWidth/totalHeight (include/ray_tracer.h
+ * :17-39).  What opencl_host.cc:42-53 baked into the kernel as -D macros are
+ * run-time parameters here. */
+typedef struct rtx_options {
+	uint32_t width, height;         /* output image */
+	float    focal_length;          /* as given; the 6-significant-digit round trip of
+	                                   compiler_options.h:13-19 is applied inside rtx_create */
+	uint32_t n_super_samples;
+	int32_t  enable_shading;        /* SHADING_ENABLE */
+	int32_t  enable_ao;             /* must be 0: AO rays are outside this path (render -a 0) */
+	float    ao_max_distance;
+	uint32_t ao_num_samples;
+	int32_t  ao_method;
+	int32_t  ao_alpha_min, ao_alpha_max;
+	int32_t  bvh_method;            /* informational */
+	uint32_t total_width, total_height; /* width/height * (unsigned)sqrt(n_super_samples); 0 = derive */
+	/* ---- extensions; all-zero reproduces the reference ---- */
+	int32_t  device;                /* CUDA device ordinal */
+	uint32_t jitter_seed;           /* 0 = regular grid (+0.5f); else hash jitter (config C3) */
+	uint32_t tile_rank, tile_world; /* interleaved 32x32-pixel tile partition; world 0/1 = whole image */
+} rtx_options;
+
+typedef struct rtx_device_info_t {
+	char     name[256];
+	int32_t  cc_major, cc_minor;
+	int32_t  sm_count;
+	int32_t  clock_khz, mem_clock_khz, mem_bus_bits;
+	uint64_t global_mem_bytes;
+	uint64_t l2_bytes;
+	uint64_t smem_per_sm_bytes, smem_per_block_optin_bytes;
+	int32_t  max_threads_per_sm, regs_per_sm;
+	int32_t  driver_version, runtime_version;
+} rtx_device_info_t;
+
+/* Statistics of the last render / trace call on the context. */
+typedef struct rtx_stats {
+	uint64_t rays;              /* rays traced by the last call (this rank's share) */
+	double   kernel_ms;         /* CUDA-event time of the traversal kernel(s) */
+	uint32_t kernel_launches;   /* kernels launched by the last call */
+	uint32_t kernel_variant;    /* RTX_KERNEL_* actually used */
+	/* device-side counters; only filled when RTX_TUNE_COUNTERS is set */
+	uint64_t node_visits;       /* boxes slab-tested */
+	uint64_t tri_tests;
+	uint64_t leafbox_tests;
+	uint64_t exact_path_rays;   /* rays routed to the reference-order walk */
+	uint32_t tree_depth;        /* depth of the flattened tree (stack need) */
+	uint32_t num_pairs;         /* internal nodes of the flattened tree */
+} rtx_stats;
+
+/* Tunables (rtx_set_tunable).  Defaults are the measured best. */
+#define RTX_TUNE_KERNEL        1  /* RTX_KERNEL_* */
+#define RTX_TUNE_LEAF_SIZE     2  /* max triangles per flattened leaf, 1..8 (takes effect at next upload) */
+#define RTX_TUNE_RECORD_HITS   3  /* 1: keep per-ray face id + distance for rtx_download_hits */
+#define RTX_TUNE_COUNTERS      4  /* 1: count node visits / triangle tests on the device (slower) */
+#define RTX_TUNE_TOP_SMEM      5  /* node pairs of the top levels staged in shared memory, 0 = off */
+#define RTX_TUNE_BLOCKS_PER_SM 6
+#define RTX_TUNE_FLATTEN_ON_DEVICE 7 /* 1: build the GPU layout with kernels, 0: on the host */
+
+#define RTX_KERNEL_PERSISTENT  0  /* persistent warps, ordered stack traversal, distance culling */
+#define RTX_KERNEL_EXHAUSTIVE  1  /* one thread per ray, the reference's stackless pre-order walk */
+
+/* ---- the reference's five calls ---- */
+
+int rtx_print_info(void);
+int rtx_device_count(int *count);
+int rtx_device_info(int device, rtx_device_info_t *info);
+
+int rtx_create(rtx_ctx **ctx, const rtx_options *options);
+
+/* All host reads finish before this returns (render.cc:96-103 clears the
+ * vectors right after).  faces: 3 vertex ids per triangle in BVH leaf order;
+ * nodes: pre-order subtree sizes, nodes[0] == nnodes; aabbs16: 2*nnodes
+ * (min,max) vectors; verts16/vnormals16: nverts == nnormals vectors. */
+int rtx_upload(rtx_ctx *ctx,
+               const uint32_t *faces, size_t nfaceidx,
+               const uint32_t *nodes, size_t nnodes,
+               const float *aabbs16, size_t naabbvec,
+               const float *verts16, size_t nverts,
+               const float *vnormals16, size_t nnormals);
+
+/* Launch the traversal over this context's share of the image and wait. */
+int rtx_render(rtx_ctx *ctx);
+
+/* total_width*total_height floats, row-major (whole image only: tile_world <= 1). */
+int rtx_download(rtx_ctx *ctx, float *image);
+
+void rtx_destroy(rtx_ctx *ctx);
+
+/* ctx may be NULL: message of the last failed call without a context. */
+const char *rtx_last_error(const rtx_ctx *ctx);
+
+/* ---- extensions needed by the configurations (not in the reference) ---- */
+
+int rtx_set_tunable(rtx_ctx *ctx, int which, int64_t value);
+int rtx_get_stats(const rtx_ctx *ctx, rtx_stats *stats);
+
+/* Enqueue the render on a CUDA stream (cudaStream_t as void*; NULL = the
+ * context's own stream) without waiting. */
+int rtx_render_async(rtx_ctx *ctx, void *stream);
+int rtx_synchronize(rtx_ctx *ctx);
+
+/* Per-ray hit triangle (3 * leaf index, the kernel's face_id; RTX_NO_HIT on
+ * miss) and hit distance (+inf on miss) of the last render; needs
+ * RTX_TUNE_RECORD_HITS.  Whole image only. */
+int rtx_download_hits(rtx_ctx *ctx, uint32_t *face_id, float *distance);
+
+/* RayTracer::resize (src/ray_tracer.cc:3-15) on the device, then a
+ * width*height byte download: the bytes render.cc:130-137 writes after the
+ * PGM header. */
+int rtx_download_u8(rtx_ctx *ctx, unsigned char *image);
+
+/* Device pointer to this context's float output: the row-major image, or
+ * with tile_world > 1 the compact [local_tile][32][32] buffer.  count =
+ * number of floats. */
+int rtx_device_image(rtx_ctx *ctx, void **device_ptr, size_t *count);
+
+/* Closest hit for arbitrary rays (config C5), reference scene_intersect
+ * semantics with the given max_distance.  origins/dirs: 4 floats per ray.
+ * Host-pointer and device-pointer forms. */
+int rtx_trace_rays(rtx_ctx *ctx, const float *origins, const float *dirs, size_t nrays, float max_distance,
+                   uint32_t *face_id, float *distance);
+int rtx_trace_rays_device(rtx_ctx *ctx, const void *d_origins, const void *d_dirs, size_t nrays, float max_distance,
+                          void *d_face_id, void *d_distance, void *stream);
+/* Rays [first, first+nrays) of the counter-based generator,
+ * generated on the device; results stay on the device unless host pointers
+ * are given (either may be NULL).  sum_face_id / hit_count: checksums. */
+int rtx_trace_random_rays(rtx_ctx *ctx, uint32_t seed, uint64_t first, size_t nrays, float max_distance,
+                          uint32_t *face_id, float *distance, uint64_t *hit_count, uint64_t *sum_face_id);
+
+/* ---- multi-GPU tile partition (one context per rank) ---- */
+
+/* Layout of the interleaved partition for an image: tiles are 32x32 pixels,
+ * tile t belongs to rank t % world.  tiles_per_rank is the padded (equal)
+ * count every rank's compact buffer holds. */
+int rtx_tile_layout(uint32_t total_width, uint32_t total_height, uint32_t world,
+                    uint32_t *tiles_x, uint32_t *tiles_y, uint32_t *tiles_per_rank);
+
+/* Scatter `world` gathered compact buffers (rank-major, tiles_per_rank*1024
+ * floats each) into the row-major image of this context (rank 0). */
+int rtx_deinterleave_async(rtx_ctx *ctx, const void *d_gathered, uint32_t world, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

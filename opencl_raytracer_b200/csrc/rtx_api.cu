@@ -1,0 +1,805 @@
+/*
+ * rtx_api.cu -- the C ABI of include/rtx_b200.h over the CUDA runtime.
+ *
+ * Replaces the reference's device host layer (src/opencl_host.cc): device
+ * pick + info dump (:15-31, :76-119), buffer creation and blocking upload
+ * (:120-136), kernel launch + finish (:137-149), blocking download
+ * (:150-153).  What the reference passed to the OpenCL JIT as -D macros
+ * (:42-53) are kernel arguments here; the kernels are compiled ahead of time
+ * for sm_100a.  There is no CPU path: without a CUDA device every call that
+ * needs one returns RTX_ERR_NO_DEVICE.
+ */
+#include "rtx_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "rtx_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t bytes = 0;
+	cudaError_t alloc(size_t n)
+	{
+		if (p && bytes >= n && bytes <= 2 * n + 4096) return cudaSuccess;
+		release();
+		if (n == 0) n = 16;
+		cudaError_t e = cudaMalloc(&p, n);
+		if (e == cudaSuccess) bytes = n; else p = nullptr;
+		return e;
+	}
+	void release()
+	{
+		if (p) cudaFree(p);
+		p = nullptr;
+		bytes = 0;
+	}
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+} /* namespace */
+
+struct rtx_ctx {
+	rtx_options opt;
+	float focal;                 /* after the compiler_options.h round trip */
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	bool ev_pending = false;
+	std::string error;
+	/* tunables */
+	int kernel = RTX_KERNEL_PERSISTENT;
+	int leaf_size = 4;
+	int record_hits = 0;
+	int counters = 0;
+	int top_smem = 0;
+	int blocks_per_sm = 0;       /* 0 = default of the variant */
+	int flatten_on_device = 0;
+	/* scene */
+	bool uploaded = false;
+	SceneDev sc{};
+	DevBuf d_pairs, d_tris, d_leafbox, d_tnormals, d_ref_nodes, d_ref_aabbs;
+	f3 bbmin{}, bbmax{};
+	uint32_t tree_depth = 0;
+	/* image */
+	uint32_t W = 0, H = 0, tiles_x = 0, tiles_y = 0, tiles_per_rank = 0, local_tiles = 0;
+	uint32_t rank = 0, world = 1;
+	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums;
+	bool rendered = false, full_valid = false;
+	/* stats */
+	rtx_stats stats{};
+};
+
+namespace {
+
+int fail(rtx_ctx *ctx, int code, const std::string &msg)
+{
+	if (ctx) ctx->error = msg;
+	g_error = msg;
+	return code;
+}
+
+int cuda_fail(rtx_ctx *ctx, cudaError_t e, const char *what)
+{
+	const bool nodev = e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice;
+	return fail(ctx, nodev ? RTX_ERR_NO_DEVICE : RTX_ERR_CUDA,
+	            std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+
+#define CU(ctx, call)                                                   \
+	do {                                                                \
+		cudaError_t e_ = (call);                                        \
+		if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);        \
+	} while (0)
+
+/* include/compiler_options.h:13-19: `ss << v` (6 significant digits) + 'f',
+ * re-read by the OpenCL front end. */
+float focal_roundtrip(float f)
+{
+	char buf[64];
+	std::snprintf(buf, sizeof buf, "%g", (double)f);
+	return std::strtof(buf, nullptr);
+}
+
+/* ----------------------------- flatten ---------------------------------- */
+
+struct Flat {
+	std::vector<float4> pairs;
+	std::vector<uint32_t> leaf_node;   /* leaf index -> reference node index */
+	uint32_t top_pairs = 0;
+	uint32_t depth = 0;
+};
+
+inline uint32_t leaves_of(uint32_t subtree_size) { return (subtree_size + 1) >> 1; }
+
+/* The invariants of SURVEY 3.3 that the traversal relies on. */
+bool validate_tree(const uint32_t *nodes, size_t n, size_t ntris, std::string &why)
+{
+	if (n == 0 || nodes[0] != n) { why = "nodes[0] must equal the node count"; return false; }
+	if ((n & 1) == 0 || leaves_of((uint32_t)n) != ntris) { why = "node count must be 2*triangles-1"; return false; }
+	for (size_t i = 0; i < n; ++i) {
+		const size_t s = nodes[i];
+		if ((s & 1) == 0 || i + s > n) { why = "subtree size out of range at node " + std::to_string(i); return false; }
+		if (s > 1) {
+			const size_t l = nodes[i + 1];
+			if ((l & 1) == 0 || l + 2 > s) { why = "left subtree size invalid at node " + std::to_string(i); return false; }
+			if (nodes[i + 1 + l] != s - 1 - l) { why = "children do not tile node " + std::to_string(i); return false; }
+		}
+	}
+	return true;
+}
+
+inline int leaf_ref(uint32_t first_tri, uint32_t count) { return (int)~((first_tri << 3) | (count - 1)); }
+
+void flatten(const uint32_t *nodes, const float *aabbs16, size_t n, int leaf_size, uint32_t top_target, Flat &out)
+{
+	const size_t ntris = leaves_of((uint32_t)n);
+	out.leaf_node.resize(ntris);
+	for (size_t i = 0, t = 0; i < n; ++i)
+		if (nodes[i] == 1) out.leaf_node[t++] = (uint32_t)i;
+
+	struct Item { uint32_t node, first_leaf, depth; int64_t patch; /* float index of the parent's ref slot, -1 = none */ };
+	auto box = [&](uint32_t node, float4 &a, float4 &b, int ref) {
+		const float *lo = aabbs16 + 8 * (size_t)node, *hi = lo + 4;
+		a = make_float4(lo[0], lo[1], lo[2], hi[0]);
+		b = make_float4(hi[1], hi[2], __builtin_bit_cast(float, ref), 0.0f);
+	};
+	out.pairs.clear();
+	out.pairs.reserve(4 * (ntris / (size_t)std::max(1, leaf_size) + 16));
+	out.depth = 0;
+
+	if (n == 1) {   /* a single triangle: pair 0 = {the leaf, an unreachable far box} */
+		float4 a, b;
+		box(0, a, b, leaf_ref(0, 1));
+		out.pairs.push_back(a); out.pairs.push_back(b);
+		out.pairs.push_back(make_float4(3e38f, 3e38f, 3e38f, 3e38f));
+		out.pairs.push_back(make_float4(3e38f, 3e38f, __builtin_bit_cast(float, leaf_ref(0, 1)), 0.0f));
+		out.top_pairs = 1;
+		out.depth = 1;
+		return;
+	}
+
+	std::deque<Item> bfs;
+	std::vector<Item> dfs;
+	bfs.push_back(Item{ 0, 0, 1, -1 });
+	bool in_bfs = true;
+	auto expand = [&](const Item &it) {
+		const uint32_t p = (uint32_t)(out.pairs.size() / 4);
+		if (it.patch >= 0) reinterpret_cast<float *>(out.pairs.data())[it.patch] = __builtin_bit_cast(float, (int)p);
+		if (it.depth > out.depth) out.depth = it.depth;
+		out.pairs.resize(out.pairs.size() + 4);
+		const uint32_t iL = it.node + 1, iR = it.node + 1 + nodes[it.node + 1];
+		const uint32_t child[2] = { iL, iR };
+		const uint32_t first[2] = { it.first_leaf, it.first_leaf + leaves_of(nodes[iL]) };
+		Item kids[2];
+		int nk = 0;
+		for (int s = 0; s < 2; ++s) {
+			const uint32_t lv = leaves_of(nodes[child[s]]);
+			float4 a, b;
+			if (lv <= (uint32_t)leaf_size) {
+				box(child[s], a, b, leaf_ref(first[s], lv));
+			} else {
+				box(child[s], a, b, 0);
+				kids[nk++] = Item{ child[s], first[s], it.depth + 1, (int64_t)(4 * (4 * (size_t)p + 2 * s + 1) + 2) };
+			}
+			out.pairs[4 * (size_t)p + 2 * s] = a;
+			out.pairs[4 * (size_t)p + 2 * s + 1] = b;
+		}
+		if (in_bfs) { for (int k = 0; k < nk; ++k) bfs.push_back(kids[k]); }
+		else { for (int k = nk - 1; k >= 0; --k) dfs.push_back(kids[k]); }
+	};
+	while (!bfs.empty() && out.pairs.size() / 4 < top_target) {
+		const Item it = bfs.front();
+		bfs.pop_front();
+		expand(it);
+	}
+	out.top_pairs = (uint32_t)(out.pairs.size() / 4);
+	in_bfs = false;
+	while (!bfs.empty()) {
+		dfs.push_back(bfs.front());
+		bfs.pop_front();
+		while (!dfs.empty()) {
+			const Item it = dfs.back();
+			dfs.pop_back();
+			expand(it);
+		}
+	}
+}
+
+/* ------------------------------ launches -------------------------------- */
+
+struct Variant { int block, min_blocks, smem_stack; };
+
+template <int BLOCK, int MINB, int SST, bool TOP, bool COUNT, bool RECORD>
+cudaError_t launch_render_t(rtx_ctx *c, const Work &w, cudaStream_t st, int blocks_per_sm)
+{
+	auto k = k_render_persistent<BLOCK, MINB, SST, TOP, COUNT, RECORD>;
+	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2) + (TOP ? (size_t)c->sc.top_pairs * 64 : 0);
+	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	int occ = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BLOCK, smem);
+	if (e != cudaSuccess) return e;
+	if (occ < 1) occ = 1;
+	if (blocks_per_sm > 0 && blocks_per_sm < occ) occ = blocks_per_sm;
+	const unsigned grid = (unsigned)(c->sm_count * occ);
+	k<<<grid, BLOCK, smem, st>>>(c->sc, w, c->d_counters.as<Counters>());
+	return cudaGetLastError();
+}
+
+template <bool TOP, bool COUNT, bool RECORD>
+cudaError_t launch_render_v(rtx_ctx *c, const Work &w, cudaStream_t st)
+{
+	return launch_render_t<256, 3, 8, TOP, COUNT, RECORD>(c, w, st, c->blocks_per_sm);
+}
+
+cudaError_t launch_render(rtx_ctx *c, const Work &w, cudaStream_t st)
+{
+	const bool top = c->top_smem > 0 && c->sc.top_pairs > 0, cnt = c->counters != 0, rec = c->record_hits != 0;
+	if (c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok) {
+		const unsigned warps_per_block = 8, grid = (w.num_units + warps_per_block - 1) / warps_per_block;
+		if (grid == 0) return cudaSuccess;
+		if (cnt) { if (rec) k_render_exhaustive<true, true><<<grid, 256, 0, st>>>(c->sc, w, c->d_counters.as<Counters>());
+		           else k_render_exhaustive<true, false><<<grid, 256, 0, st>>>(c->sc, w, c->d_counters.as<Counters>()); }
+		else     { if (rec) k_render_exhaustive<false, true><<<grid, 256, 0, st>>>(c->sc, w, c->d_counters.as<Counters>());
+		           else k_render_exhaustive<false, false><<<grid, 256, 0, st>>>(c->sc, w, c->d_counters.as<Counters>()); }
+		return cudaGetLastError();
+	}
+#define RTX_DISPATCH(T, C, R) if (top == T && cnt == C && rec == R) return launch_render_v<T, C, R>(c, w, st)
+	RTX_DISPATCH(false, false, false); RTX_DISPATCH(false, false, true);
+	RTX_DISPATCH(false, true, false);  RTX_DISPATCH(false, true, true);
+	RTX_DISPATCH(true, false, false);  RTX_DISPATCH(true, false, true);
+	RTX_DISPATCH(true, true, false);   RTX_DISPATCH(true, true, true);
+#undef RTX_DISPATCH
+	return cudaErrorInvalidValue;
+}
+
+template <bool TOP, bool COUNT>
+cudaError_t launch_rays_t(rtx_ctx *c, const RayWork &w, cudaStream_t st)
+{
+	constexpr int BLOCK = 256, MINB = 3, SST = 8;
+	auto k = k_trace_rays<BLOCK, MINB, SST, TOP, COUNT>;
+	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2) + (TOP ? (size_t)c->sc.top_pairs * 64 : 0);
+	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	int occ = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BLOCK, smem);
+	if (e != cudaSuccess) return e;
+	if (occ < 1) occ = 1;
+	if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
+	k<<<(unsigned)(c->sm_count * occ), BLOCK, smem, st>>>(c->sc, w, c->d_counters.as<Counters>());
+	return cudaGetLastError();
+}
+
+cudaError_t launch_rays(rtx_ctx *c, const RayWork &w, cudaStream_t st)
+{
+	const bool top = c->top_smem > 0 && c->sc.top_pairs > 0, cnt = c->counters != 0;
+	if (top) return cnt ? launch_rays_t<true, true>(c, w, st) : launch_rays_t<true, false>(c, w, st);
+	return cnt ? launch_rays_t<false, true>(c, w, st) : launch_rays_t<false, false>(c, w, st);
+}
+
+int finish_stats(rtx_ctx *c)
+{
+	if (c->ev_pending) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->stats.kernel_ms = ms;
+		c->ev_pending = false;
+	}
+	if (c->counters) {
+		Counters h{};
+		CU(c, cudaMemcpy(&h, c->d_counters.p, sizeof h, cudaMemcpyDeviceToHost));
+		c->stats.node_visits = h.node_visits;
+		c->stats.tri_tests = h.tri_tests;
+		c->stats.leafbox_tests = h.leafbox_tests;
+		c->stats.exact_path_rays = h.exact_rays;
+	}
+	return RTX_OK;
+}
+
+} /* namespace */
+
+extern "C" {
+
+const char *rtx_last_error(const rtx_ctx *ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+
+int rtx_device_count(int *count)
+{
+	if (!count) return fail(nullptr, RTX_ERR_ARG, "null count");
+	*count = 0;
+	cudaError_t e = cudaGetDeviceCount(count);
+	if (e != cudaSuccess) { *count = 0; return cuda_fail(nullptr, e, "cudaGetDeviceCount"); }
+	return *count > 0 ? RTX_OK : fail(nullptr, RTX_ERR_NO_DEVICE, "No device found");
+}
+
+int rtx_device_info(int device, rtx_device_info_t *info)
+{
+	if (!info) return fail(nullptr, RTX_ERR_ARG, "null info");
+	std::memset(info, 0, sizeof *info);
+	cudaDeviceProp p;
+	CU(nullptr, cudaGetDeviceProperties(&p, device));
+	std::snprintf(info->name, sizeof info->name, "%s", p.name);
+	info->cc_major = p.major;
+	info->cc_minor = p.minor;
+	info->sm_count = p.multiProcessorCount;
+	cudaDeviceGetAttribute(&info->clock_khz, cudaDevAttrClockRate, device);
+	cudaDeviceGetAttribute(&info->mem_clock_khz, cudaDevAttrMemoryClockRate, device);
+	info->mem_bus_bits = p.memoryBusWidth;
+	info->global_mem_bytes = p.totalGlobalMem;
+	info->l2_bytes = (uint64_t)p.l2CacheSize;
+	info->smem_per_sm_bytes = p.sharedMemPerMultiprocessor;
+	info->smem_per_block_optin_bytes = p.sharedMemPerBlockOptin;
+	info->max_threads_per_sm = p.maxThreadsPerMultiProcessor;
+	info->regs_per_sm = p.regsPerMultiprocessor;
+	cudaDriverGetVersion(&info->driver_version);
+	cudaRuntimeGetVersion(&info->runtime_version);
+	return RTX_OK;
+}
+
+/* opencl_host.cc:76-119 prints a tree of platforms and devices; the shadow
+ * OpenCLHost::printInfo() formats rtx_device_info through the reference's own
+ * Info class.  This plain-text form is for C callers. */
+int rtx_print_info(void)
+{
+	int n = 0;
+	const int rc = rtx_device_count(&n);
+	if (rc != RTX_OK) { std::printf("Hardware information: no CUDA device (%s)\n", g_error.c_str()); return rc; }
+	std::printf("*** Hardware information ***\n");
+	for (int d = 0; d < n; ++d) {
+		rtx_device_info_t i;
+		if (rtx_device_info(d, &i) != RTX_OK) continue;
+		std::printf("Device #%d\n  Name................... %s\n  Compute capability..... %d.%d\n  Max compute units...... %d\n"
+		            "  Global memory (MiB).... %llu\n  L2 cache (MiB)......... %llu\n  Local memory size (B).. %llu\n"
+		            "  Driver / runtime....... %d / %d\n",
+		            d, i.name, i.cc_major, i.cc_minor, i.sm_count, (unsigned long long)(i.global_mem_bytes >> 20),
+		            (unsigned long long)(i.l2_bytes >> 20), (unsigned long long)i.smem_per_block_optin_bytes,
+		            i.driver_version, i.runtime_version);
+	}
+	return RTX_OK;
+}
+
+int rtx_tile_layout(uint32_t total_width, uint32_t total_height, uint32_t world, uint32_t *tiles_x, uint32_t *tiles_y,
+                    uint32_t *tiles_per_rank)
+{
+	if (world == 0) world = 1;
+	const uint32_t tx = (total_width + RTX_TILE - 1) / RTX_TILE, ty = (total_height + RTX_TILE - 1) / RTX_TILE;
+	if (tiles_x) *tiles_x = tx;
+	if (tiles_y) *tiles_y = ty;
+	if (tiles_per_rank) *tiles_per_rank = (uint32_t)(((uint64_t)tx * ty + world - 1) / world);
+	return RTX_OK;
+}
+
+int rtx_create(rtx_ctx **out, const rtx_options *options)
+{
+	if (!out || !options) return fail(nullptr, RTX_ERR_ARG, "null argument");
+	*out = nullptr;
+	if (options->enable_ao && options->ao_num_samples > 0)
+		return fail(nullptr, RTX_ERR_UNSUPPORTED, "ambient occlusion is outside this path: run with -a 0");
+	if (options->width == 0 || options->height == 0) return fail(nullptr, RTX_ERR_ARG, "empty image");
+	int ndev = 0;
+	const int rc = rtx_device_count(&ndev);
+	if (rc != RTX_OK) return rc;
+	if (options->device < 0 || options->device >= ndev) return fail(nullptr, RTX_ERR_NO_DEVICE, "device ordinal out of range");
+
+	rtx_ctx *c = new rtx_ctx;
+	c->opt = *options;
+	c->device = options->device;
+	c->focal = focal_roundtrip(options->focal_length);
+	const unsigned n = (unsigned)std::sqrt((double)options->n_super_samples);   /* ray_tracer.h:33-34 */
+	c->W = options->total_width ? options->total_width : options->width * n;
+	c->H = options->total_height ? options->total_height : options->height * n;
+	c->world = options->tile_world > 1 ? options->tile_world : 1;
+	c->rank = c->world > 1 ? options->tile_rank : 0;
+	if (c->rank >= c->world || c->W == 0 || c->H == 0) { delete c; return fail(nullptr, RTX_ERR_ARG, "bad tile partition or image size"); }
+	rtx_tile_layout(c->W, c->H, c->world, &c->tiles_x, &c->tiles_y, &c->tiles_per_rank);
+	const uint64_t ntiles = (uint64_t)c->tiles_x * c->tiles_y;
+	c->local_tiles = (uint32_t)((ntiles + c->world - 1 - c->rank) / c->world);
+	if (ntiles * 32 >= 0xffffffffull) { delete c; return fail(nullptr, RTX_ERR_ARG, "image too large"); }
+
+	auto bail = [&](cudaError_t e, const char *what) { const int r = cuda_fail(nullptr, e, what); rtx_destroy(c); return r; };
+	cudaError_t e;
+	if ((e = cudaSetDevice(c->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+	cudaDeviceProp p;
+	if ((e = cudaGetDeviceProperties(&p, c->device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+	c->sm_count = p.multiProcessorCount;
+	if (p.major < 10) {
+		rtx_destroy(c);
+		return fail(nullptr, RTX_ERR_NO_DEVICE, std::string("kernels are built for sm_100a only; device is ") + p.name);
+	}
+	if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+	if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+	if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+	const size_t out_floats = c->world > 1 ? (size_t)c->tiles_per_rank * RTX_TILE * RTX_TILE : (size_t)c->W * c->H;
+	if ((e = c->d_image.alloc(out_floats * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc(image)");
+	if ((e = c->d_counter.alloc(sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc(counter)");
+	if ((e = c->d_counters.alloc(sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMalloc(counters)");
+	if ((e = c->d_sums.alloc(2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc(sums)");
+	if ((e = cudaMemsetAsync(c->d_image.p, 0, out_floats * sizeof(float), c->stream)) != cudaSuccess) return bail(e, "cudaMemset");
+	*out = c;
+	return RTX_OK;
+}
+
+void rtx_destroy(rtx_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	DevBuf *bufs[] = { &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
+	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums };
+	for (DevBuf *b : bufs) b->release();
+	if (c->ev0) cudaEventDestroy(c->ev0);
+	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int rtx_set_tunable(rtx_ctx *c, int which, int64_t v)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	switch (which) {
+	case RTX_TUNE_KERNEL:
+		if (v != RTX_KERNEL_PERSISTENT && v != RTX_KERNEL_EXHAUSTIVE) return fail(c, RTX_ERR_ARG, "unknown kernel");
+		c->kernel = (int)v; break;
+	case RTX_TUNE_LEAF_SIZE:
+		if (v < 1 || v > 8) return fail(c, RTX_ERR_ARG, "leaf size must be 1..8");
+		c->leaf_size = (int)v; break;
+	case RTX_TUNE_RECORD_HITS: c->record_hits = v != 0; break;
+	case RTX_TUNE_COUNTERS: c->counters = v != 0; break;
+	case RTX_TUNE_TOP_SMEM:
+		if (v < 0 || v > 1024) return fail(c, RTX_ERR_ARG, "top_smem must be 0..1024 pairs");
+		c->top_smem = (int)v; break;
+	case RTX_TUNE_BLOCKS_PER_SM: c->blocks_per_sm = (int)v; break;
+	case RTX_TUNE_FLATTEN_ON_DEVICE: c->flatten_on_device = v != 0; break;
+	default: return fail(c, RTX_ERR_ARG, "unknown tunable");
+	}
+	return RTX_OK;
+}
+
+int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_t *nodes, size_t nnodes,
+               const float *aabbs16, size_t naabbvec, const float *verts16, size_t nverts,
+               const float *vnormals16, size_t nnormals)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (!faces || !nodes || !aabbs16 || !verts16 || !vnormals16) return fail(c, RTX_ERR_ARG, "null array");
+	if (nfaceidx == 0 || nfaceidx % 3 != 0) return fail(c, RTX_ERR_ARG, "faces must hold 3 indices per triangle");
+	const size_t ntris = nfaceidx / 3;
+	if (naabbvec != 2 * nnodes) return fail(c, RTX_ERR_ARG, "aabbs must hold 2 vectors per node");
+	if (nverts != nnormals || nverts == 0) return fail(c, RTX_ERR_ARG, "one normal per vertex required");
+	if (ntris >= (1u << 28)) return fail(c, RTX_ERR_ARG, "too many triangles (limit 2^28)");
+	std::string why;
+	if (!validate_tree(nodes, nnodes, ntris, why)) return fail(c, RTX_ERR_ARG, "malformed BVH: " + why);
+	for (size_t i = 0; i < nfaceidx; ++i)
+		if (faces[i] >= nverts) return fail(c, RTX_ERR_ARG, "face index out of range");
+	CU(c, cudaSetDevice(c->device));
+	c->uploaded = false;
+
+	Flat flat;
+	flatten(nodes, aabbs16, nnodes, c->leaf_size, c->top_smem > 0 ? (uint32_t)c->top_smem : 0u, flat);
+
+	DevBuf d_faces, d_verts, d_vnormals, d_leaf_node;
+	auto cleanup = [&] { d_faces.release(); d_verts.release(); d_vnormals.release(); d_leaf_node.release(); };
+#define CUU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(c, e_, #call); } } while (0)
+	CUU(d_faces.alloc(nfaceidx * 4));
+	CUU(d_verts.alloc(nverts * 16));
+	CUU(d_vnormals.alloc(nverts * 16));
+	CUU(d_leaf_node.alloc(ntris * 4));
+	CUU(c->d_ref_nodes.alloc(nnodes * 4));
+	CUU(c->d_ref_aabbs.alloc(nnodes * 32));
+	CUU(c->d_pairs.alloc(flat.pairs.size() * 16));
+	CUU(c->d_tris.alloc(ntris * 64));
+	CUU(c->d_leafbox.alloc(ntris * 32));
+	CUU(c->d_tnormals.alloc(ntris * 48));
+	cudaStream_t st = c->stream;
+	CUU(cudaMemcpyAsync(d_faces.p, faces, nfaceidx * 4, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(d_verts.p, verts16, nverts * 16, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(d_vnormals.p, vnormals16, nverts * 16, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->d_ref_nodes.p, nodes, nnodes * 4, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->d_ref_aabbs.p, aabbs16, nnodes * 32, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(d_leaf_node.p, flat.leaf_node.data(), ntris * 4, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->d_pairs.p, flat.pairs.data(), flat.pairs.size() * 16, cudaMemcpyHostToDevice, st));
+	k_build_triangles<<<(unsigned)((ntris + 255) / 256), 256, 0, st>>>(
+		d_faces.as<uint32_t>(), d_verts.as<float4>(), d_vnormals.as<float4>(), d_leaf_node.as<uint32_t>(),
+		c->d_ref_aabbs.as<float4>(), (uint32_t)ntris, c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>());
+	CUU(cudaGetLastError());
+	CUU(cudaStreamSynchronize(st));     /* the caller frees its arrays right after (render.cc:96-103) */
+	cleanup();
+#undef CUU
+
+	c->sc.pairs = c->d_pairs.as<float4>();
+	c->sc.tris = c->d_tris.as<float4>();
+	c->sc.leafbox = c->d_leafbox.as<float4>();
+	c->sc.tnormals = c->d_tnormals.as<float4>();
+	c->sc.ref_nodes = c->d_ref_nodes.as<uint32_t>();
+	c->sc.ref_aabbs = c->d_ref_aabbs.as<float4>();
+	c->sc.num_pairs = (uint32_t)(flat.pairs.size() / 4);
+	c->sc.top_pairs = c->top_smem > 0 ? flat.top_pairs : 0;
+	c->sc.num_tris = (uint32_t)ntris;
+	c->sc.verify_leafbox = c->leaf_size > 1 ? 1u : 0u;
+	c->bbmin = make_f3(aabbs16[0], aabbs16[1], aabbs16[2]);
+	c->bbmax = make_f3(aabbs16[4], aabbs16[5], aabbs16[6]);
+	float scale = 0.f;
+	for (int k = 0; k < 3; ++k) scale = std::fmax(scale, std::fmax(std::fabs(aabbs16[k]), std::fabs(aabbs16[4 + k])));
+	c->sc.scene_scale = scale;
+	c->tree_depth = flat.depth;
+	c->stats.tree_depth = flat.depth;
+	c->stats.num_pairs = c->sc.num_pairs;
+	c->uploaded = true;
+	c->rendered = false;
+	return RTX_OK;
+}
+
+static int enqueue_render(rtx_ctx *c, cudaStream_t st)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (!c->uploaded) return fail(c, RTX_ERR_STATE, "render before upload");
+	CU(c, cudaSetDevice(c->device));
+	const size_t out_n = c->world > 1 ? (size_t)c->tiles_per_rank * RTX_TILE * RTX_TILE : (size_t)c->W * c->H;
+	if (c->record_hits) {
+		CU(c, c->d_face_id.alloc(out_n * 4));
+		CU(c, c->d_dist.alloc(out_n * 4));
+	}
+	Work w{};
+	w.cam.W = c->W;
+	w.cam.H = c->H;
+	w.cam.a = c->focal * (float)(c->W < c->H ? c->H : c->W);        /* intersect_kernel.cl:285 */
+	w.cam.w_over_2a = (float)c->W / (2.0f * w.cam.a);               /* :287 */
+	w.cam.h_over_2a = (float)c->H / (2.0f * w.cam.a);               /* :288 */
+	w.cam.jitter_seed = c->opt.jitter_seed;
+	w.cam.shading = c->opt.enable_shading ? 1 : 0;
+	w.tiles_x = c->tiles_x;
+	w.tiles_y = c->tiles_y;
+	w.rank = c->rank;
+	w.world = c->world;
+	w.local_tiles = c->local_tiles;
+	w.num_units = c->local_tiles * 32u;
+	w.counter = c->d_counter.as<unsigned int>();
+	w.image = c->d_image.as<float>();
+	w.face_id = c->record_hits ? c->d_face_id.as<uint32_t>() : nullptr;
+	w.dist = c->record_hits ? c->d_dist.as<float>() : nullptr;
+	w.ordered_ok = c->tree_depth <= RTX_STACK_MAX ? 1 : 0;
+	CU(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
+	if (c->counters) CU(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(Counters), st));
+	CU(c, cudaEventRecord(c->ev0, st));
+	CU(c, launch_render(c, w, st));
+	CU(c, cudaEventRecord(c->ev1, st));
+	c->ev_pending = true;
+	c->stats.rays = (uint64_t)c->local_tiles * RTX_TILE * RTX_TILE;
+	if (c->world == 1) c->stats.rays = (uint64_t)c->W * c->H;
+	c->stats.kernel_launches = 1;
+	c->stats.kernel_variant = (c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
+	c->rendered = true;
+	c->full_valid = false;
+	return RTX_OK;
+}
+
+int rtx_render_async(rtx_ctx *c, void *stream)
+{
+	return enqueue_render(c, stream ? static_cast<cudaStream_t>(stream) : (c ? c->stream : nullptr));
+}
+
+int rtx_synchronize(rtx_ctx *c)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaDeviceSynchronize());
+	return finish_stats(c);
+}
+
+int rtx_render(rtx_ctx *c)
+{
+	const int rc = enqueue_render(c, c ? c->stream : nullptr);
+	if (rc != RTX_OK) return rc;
+	CU(c, cudaStreamSynchronize(c->stream));   /* queue.finish(), opencl_host.cc:147 */
+	return finish_stats(c);
+}
+
+int rtx_get_stats(const rtx_ctx *c, rtx_stats *stats)
+{
+	if (!c || !stats) return fail(nullptr, RTX_ERR_ARG, "null argument");
+	rtx_ctx *m = const_cast<rtx_ctx *>(c);
+	if (m->ev_pending && cudaEventQuery(m->ev1) == cudaSuccess) finish_stats(m);
+	*stats = c->stats;
+	return RTX_OK;
+}
+
+int rtx_device_image(rtx_ctx *c, void **device_ptr, size_t *count)
+{
+	if (!c || !device_ptr) return fail(c, RTX_ERR_ARG, "null argument");
+	if (c->world > 1 && c->full_valid) {
+		*device_ptr = c->d_image_full.p;
+		if (count) *count = (size_t)c->W * c->H;
+		return RTX_OK;
+	}
+	*device_ptr = c->d_image.p;
+	if (count) *count = c->world > 1 ? (size_t)c->tiles_per_rank * RTX_TILE * RTX_TILE : (size_t)c->W * c->H;
+	return RTX_OK;
+}
+
+static const float *full_image(rtx_ctx *c)
+{
+	if (c->world == 1) return c->d_image.as<float>();
+	return c->full_valid ? c->d_image_full.as<float>() : nullptr;
+}
+
+int rtx_download(rtx_ctx *c, float *image)
+{
+	if (!c || !image) return fail(c, RTX_ERR_ARG, "null argument");
+	if (!c->rendered && !c->full_valid) return fail(c, RTX_ERR_STATE, "download before render");
+	const float *src = full_image(c);
+	if (!src) return fail(c, RTX_ERR_STATE, "this rank holds a tile partition; gather and de-interleave first");
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaStreamSynchronize(c->stream));
+	CU(c, cudaMemcpy(image, src, (size_t)c->W * c->H * sizeof(float), cudaMemcpyDeviceToHost)); /* opencl_host.cc:151 */
+	return RTX_OK;
+}
+
+int rtx_download_hits(rtx_ctx *c, uint32_t *face_id, float *distance)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (!c->rendered || !c->record_hits || !c->d_face_id.p) return fail(c, RTX_ERR_STATE, "set RTX_TUNE_RECORD_HITS and render first");
+	if (c->world > 1) return fail(c, RTX_ERR_STATE, "hit download needs the whole image on one context");
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaStreamSynchronize(c->stream));
+	const size_t n = (size_t)c->W * c->H;
+	if (face_id) CU(c, cudaMemcpy(face_id, c->d_face_id.p, n * 4, cudaMemcpyDeviceToHost));
+	if (distance) CU(c, cudaMemcpy(distance, c->d_dist.p, n * 4, cudaMemcpyDeviceToHost));
+	return RTX_OK;
+}
+
+int rtx_download_u8(rtx_ctx *c, unsigned char *image)
+{
+	if (!c || !image) return fail(c, RTX_ERR_ARG, "null argument");
+	const float *src = full_image(c);
+	if (!src || (!c->rendered && !c->full_valid)) return fail(c, RTX_ERR_STATE, "no complete image on this context");
+	const uint32_t n = (uint32_t)std::sqrt((double)c->opt.n_super_samples);
+	const uint32_t w = c->opt.width, h = c->opt.height;
+	if (n == 0 || (uint64_t)w * n > c->W || (uint64_t)h * n > c->H) return fail(c, RTX_ERR_ARG, "image smaller than width*n x height*n");
+	CU(c, cudaSetDevice(c->device));
+	CU(c, c->d_u8.alloc((size_t)w * h));
+	const dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+	k_resize_u8<<<grid, block, 0, c->stream>>>(src, c->W, w, h, n, c->d_u8.as<unsigned char>());
+	CU(c, cudaGetLastError());
+	CU(c, cudaMemcpyAsync(image, c->d_u8.p, (size_t)w * h, cudaMemcpyDeviceToHost, c->stream));
+	CU(c, cudaStreamSynchronize(c->stream));
+	return RTX_OK;
+}
+
+int rtx_deinterleave_async(rtx_ctx *c, const void *d_gathered, uint32_t world, void *stream)
+{
+	if (!c || !d_gathered || world == 0) return fail(c, RTX_ERR_ARG, "null argument");
+	CU(c, cudaSetDevice(c->device));
+	CU(c, c->d_image_full.alloc((size_t)c->W * c->H * sizeof(float)));
+	uint32_t tx, ty, tpr;
+	rtx_tile_layout(c->W, c->H, world, &tx, &ty, &tpr);
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+	k_deinterleave<<<tx * ty, 256, 0, st>>>(static_cast<const float *>(d_gathered), world, tpr, tx, ty, c->W, c->H,
+	                                         c->d_image_full.as<float>());
+	CU(c, cudaGetLastError());
+	c->full_valid = true;
+	return RTX_OK;
+}
+
+int rtx_trace_rays_device(rtx_ctx *c, const void *d_origins, const void *d_dirs, size_t nrays, float max_distance,
+                          void *d_face_id, void *d_distance, void *stream)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (!c->uploaded) return fail(c, RTX_ERR_STATE, "trace before upload");
+	if (nrays == 0) return RTX_OK;
+	if (!d_origins || !d_dirs) return fail(c, RTX_ERR_ARG, "null ray arrays");
+	if (nrays >= (1ull << 36)) return fail(c, RTX_ERR_ARG, "too many rays in one call");
+	CU(c, cudaSetDevice(c->device));
+	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+	RayWork w{};
+	w.origins = static_cast<const float4 *>(d_origins);
+	w.dirs = static_cast<const float4 *>(d_dirs);
+	w.nrays = nrays;
+	w.max_distance = max_distance;
+	w.counter = c->d_counter.as<unsigned int>();
+	w.face_id = static_cast<uint32_t *>(d_face_id);
+	w.dist = static_cast<float *>(d_distance);
+	w.ordered_ok = c->tree_depth <= RTX_STACK_MAX ? 1 : 0;
+	w.exhaustive = c->kernel == RTX_KERNEL_EXHAUSTIVE;
+	CU(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
+	if (c->counters) CU(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(Counters), st));
+	CU(c, cudaEventRecord(c->ev0, st));
+	CU(c, launch_rays(c, w, st));
+	CU(c, cudaEventRecord(c->ev1, st));
+	c->ev_pending = true;
+	c->stats.rays = nrays;
+	c->stats.kernel_launches = 1;
+	c->stats.kernel_variant = (w.exhaustive || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
+	return RTX_OK;
+}
+
+int rtx_trace_rays(rtx_ctx *c, const float *origins, const float *dirs, size_t nrays, float max_distance,
+                   uint32_t *face_id, float *distance)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (!c->uploaded) return fail(c, RTX_ERR_STATE, "trace before upload");
+	if (nrays == 0) return RTX_OK;
+	if (!origins || !dirs) return fail(c, RTX_ERR_ARG, "null ray arrays");
+	CU(c, cudaSetDevice(c->device));
+	DevBuf d_o, d_d, d_f, d_t;
+	auto cleanup = [&] { d_o.release(); d_d.release(); d_f.release(); d_t.release(); };
+	int rc = RTX_OK;
+	cudaError_t e;
+	if ((e = d_o.alloc(nrays * 16)) != cudaSuccess || (e = d_d.alloc(nrays * 16)) != cudaSuccess ||
+	    (e = d_f.alloc(nrays * 4)) != cudaSuccess || (e = d_t.alloc(nrays * 4)) != cudaSuccess) {
+		cleanup();
+		return cuda_fail(c, e, "cudaMalloc(rays)");
+	}
+	if ((e = cudaMemcpyAsync(d_o.p, origins, nrays * 16, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+	    (e = cudaMemcpyAsync(d_d.p, dirs, nrays * 16, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) {
+		cleanup();
+		return cuda_fail(c, e, "cudaMemcpy(rays)");
+	}
+	rc = rtx_trace_rays_device(c, d_o.p, d_d.p, nrays, max_distance, d_f.p, d_t.p, nullptr);
+	if (rc == RTX_OK) {
+		if (face_id && (e = cudaMemcpyAsync(face_id, d_f.p, nrays * 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) rc = cuda_fail(c, e, "cudaMemcpy(face_id)");
+		if (rc == RTX_OK && distance && (e = cudaMemcpyAsync(distance, d_t.p, nrays * 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) rc = cuda_fail(c, e, "cudaMemcpy(distance)");
+	}
+	e = cudaStreamSynchronize(c->stream);
+	if (rc == RTX_OK && e != cudaSuccess) rc = cuda_fail(c, e, "cudaStreamSynchronize");
+	cleanup();
+	if (rc == RTX_OK) rc = finish_stats(c);
+	return rc;
+}
+
+int rtx_trace_random_rays(rtx_ctx *c, uint32_t seed, uint64_t first, size_t nrays, float max_distance,
+                          uint32_t *face_id, float *distance, uint64_t *hit_count, uint64_t *sum_face_id)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (!c->uploaded) return fail(c, RTX_ERR_STATE, "trace before upload");
+	if (hit_count) *hit_count = 0;
+	if (sum_face_id) *sum_face_id = 0;
+	if (nrays == 0) return RTX_OK;
+	if (nrays >= (1ull << 36)) return fail(c, RTX_ERR_ARG, "too many rays in one call");
+	CU(c, cudaSetDevice(c->device));
+	if (face_id) CU(c, c->d_face_id.alloc(nrays * 4));
+	if (distance) CU(c, c->d_dist.alloc(nrays * 4));
+	cudaStream_t st = c->stream;
+	RayWork w{};
+	w.seed = seed;
+	w.first = first;
+	w.nrays = nrays;
+	w.bbmin = c->bbmin;
+	w.bbmax = c->bbmax;
+	w.max_distance = max_distance;
+	w.counter = c->d_counter.as<unsigned int>();
+	w.face_id = face_id ? c->d_face_id.as<uint32_t>() : nullptr;
+	w.dist = distance ? c->d_dist.as<float>() : nullptr;
+	w.hit_count = c->d_sums.as<unsigned long long>();
+	w.sum_face_id = c->d_sums.as<unsigned long long>() + 1;
+	w.ordered_ok = c->tree_depth <= RTX_STACK_MAX ? 1 : 0;
+	w.exhaustive = c->kernel == RTX_KERNEL_EXHAUSTIVE;
+	CU(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
+	CU(c, cudaMemsetAsync(c->d_sums.p, 0, 2 * sizeof(unsigned long long), st));
+	if (c->counters) CU(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(Counters), st));
+	CU(c, cudaEventRecord(c->ev0, st));
+	CU(c, launch_rays(c, w, st));
+	CU(c, cudaEventRecord(c->ev1, st));
+	c->ev_pending = true;
+	unsigned long long sums[2] = { 0, 0 };
+	CU(c, cudaMemcpyAsync(sums, c->d_sums.p, sizeof sums, cudaMemcpyDeviceToHost, st));
+	if (face_id) CU(c, cudaMemcpyAsync(face_id, c->d_face_id.p, nrays * 4, cudaMemcpyDeviceToHost, st));
+	if (distance) CU(c, cudaMemcpyAsync(distance, c->d_dist.p, nrays * 4, cudaMemcpyDeviceToHost, st));
+	CU(c, cudaStreamSynchronize(st));
+	if (hit_count) *hit_count = sums[0];
+	if (sum_face_id) *sum_face_id = sums[1];
+	c->stats.rays = nrays;
+	c->stats.kernel_launches = 1;
+	c->stats.kernel_variant = (w.exhaustive || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
+	c->rendered = false;
+	return finish_stats(c);
+}
+
+} /* extern "C" */

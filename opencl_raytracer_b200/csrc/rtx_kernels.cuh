@@ -1,0 +1,455 @@
+/*
+ * rtx_kernels.cuh -- traversal kernels (sm_100a).
+ *
+ * Device scene layout (built by rtx_api.cu::flatten from the reference's
+ * upload arrays; DESIGN.md "Data layout"):
+ *
+ *   pairs     4 x float4 per INTERNAL node of the flattened tree = its two
+ *             children as two 32-byte nodes {lo.xyz, hi.xyz, ref, pad}:
+ *               q0 = (L.lo.x, L.lo.y, L.lo.z, L.hi.x)
+ *               q1 = (L.hi.y, L.hi.z, bits(L.ref), 0)
+ *               q2, q3 = the same for R
+ *             ref >= 0: index of the child's own pair; ref < 0: leaf,
+ *             ~ref = (first_triangle << 3) | (count - 1), count <= 8.
+ *             Pairs [0, top_pairs) are the top levels in breadth-first order
+ *             (staged in shared memory), the rest depth-first.
+ *   tris      4 x float4 per triangle in leaf order (rtx_device.cuh)
+ *   leafbox   2 x float4 per triangle: its reference leaf AABB (min, max)
+ *   tnormals  3 x float4 per triangle: the three corner normals, pre-gathered
+ *   ref_nodes / ref_aabbs   the reference's own arrays, for the literal
+ *             stackless walk (exhaustive kernel, NaN-slab rays, deep trees)
+ */
+#pragma once
+#include "rtx_device.cuh"
+
+struct SceneDev {
+	const float4 *pairs;
+	const float4 *tris;
+	const float4 *leafbox;
+	const float4 *tnormals;
+	const uint32_t *ref_nodes;
+	const float4 *ref_aabbs;
+	uint32_t num_pairs;
+	uint32_t top_pairs;       /* pairs staged in shared memory */
+	uint32_t num_tris;
+	uint32_t verify_leafbox;  /* leaves hold > 1 triangle: per-triangle leaf box must be checked */
+	float scene_scale;        /* max |coordinate| of the root box */
+};
+
+struct Counters {
+	unsigned long long node_visits, tri_tests, leafbox_tests, exact_rays;
+};
+
+struct HitRec {
+	float dist;      /* +inf = miss */
+	uint32_t tri;    /* leaf index */
+	float s, t;
+};
+
+#define RTX_STACK_MAX 64          /* deeper flattened trees use the stackless walk */
+#define RTX_TILE 32               /* partition / scheduling tile: 32 x 32 pixels */
+
+/* --------------------------------------------------------------------------
+ * The reference's walk, literally (intersect_kernel.cl:184-213): pre-order
+ * array, subtree skip on box miss, no culling, strict `>` update so the first
+ * triangle in leaf order wins ties.
+ * ------------------------------------------------------------------------ */
+template <bool COUNT>
+RTX_DEV void walk_reference(const SceneDev &sc, f3 o, f3 d, float max_distance, HitRec &best, Counters *cnt)
+{
+	const uint32_t n = __ldg(sc.ref_nodes);
+	uint32_t tri = 0;
+	unsigned long long visits = 0, tests = 0;
+	for (uint32_t i = 0; i < n;) {
+		const uint32_t node_count = __ldg(sc.ref_nodes + i);
+		const float4 lo = __ldg(sc.ref_aabbs + 2 * (size_t)i);
+		const float4 hi = __ldg(sc.ref_aabbs + 2 * (size_t)i + 1);
+		if (COUNT) ++visits;
+		if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), o, d, max_distance)) {
+			tri += (node_count + 1) >> 1;
+			i += node_count;
+		} else {
+			if (node_count == 1) {
+				const float4 *q = sc.tris + 4 * (size_t)tri;
+				TriHit h;
+				if (COUNT) ++tests;
+				if (triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, __int_as_float(0x7f800000), h)) {
+					if (best.dist > h.dist) { best.dist = h.dist; best.tri = tri; best.s = h.s; best.t = h.t; }
+				}
+				++tri;
+			}
+			++i;
+		}
+	}
+	if (COUNT) {
+		atomicAdd(&cnt->node_visits, visits);
+		atomicAdd(&cnt->tri_tests, tests);
+	}
+}
+
+/* --------------------------------------------------------------------------
+ * Ordered stack traversal with distance culling.  Same result as the walk
+ * above (DESIGN.md "Why re-ordering is exact"):
+ *   - a triangle is tested by the reference iff its leaf box passes the slab
+ *     test (ancestor boxes contain it, and the test is monotone); interior
+ *     boxes here are those same boxes, tested in min/max form, which decides
+ *     identically whenever no 0*inf occurs -- rays with a zero direction
+ *     component never enter this function;
+ *   - with > 1 triangle per leaf the per-triangle leaf box is tested, with
+ *     the literal form, before a hit is accepted;
+ *   - closest hit = min distance, ties -> smallest leaf index;
+ *   - a subtree/triangle is culled only if its entry parameter exceeds the
+ *     best hit's parameter by a margin far larger than any rounding.
+ * ------------------------------------------------------------------------ */
+struct Slab { float tmin, tmax; };
+
+RTX_DEV Slab slab_minmax(float lx, float ly, float lz, float hx, float hy, float hz, f3 o, f3 id)
+{
+	const float ax = rn_mul(rn_sub(lx, o.x), id.x), bx = rn_mul(rn_sub(hx, o.x), id.x);
+	const float ay = rn_mul(rn_sub(ly, o.y), id.y), by = rn_mul(rn_sub(hy, o.y), id.y);
+	const float az = rn_mul(rn_sub(lz, o.z), id.z), bz = rn_mul(rn_sub(hz, o.z), id.z);
+	Slab s;
+	s.tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+	s.tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+	return s;
+}
+
+template <int SMEM_STACK, bool TOP_SMEM, bool COUNT>
+RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ s_top, uint2 *__restrict__ s_stack,
+                              f3 o, f3 d, float max_distance, HitRec &best, Counters *cnt)
+{
+	const f3 id = make_f3(rn_div(1.0f, d.x), rn_div(1.0f, d.y), rn_div(1.0f, d.z));
+	/* culling margins in ray-parameter units */
+	const float inv_len = rsqrtf(fmaxf(d.x * d.x + d.y * d.y + d.z * d.z, 1e-30f));
+	const float scale = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), sc.scene_scale));
+	const float abs_margin = 1e-5f * scale * inv_len;
+	float limit = max_distance;          /* boxes/triangles entering beyond this cannot win */
+	float best_r = __int_as_float(0x7f800000);
+	uint2 l_stack[RTX_STACK_MAX - SMEM_STACK];
+	int sp = 0;
+	int cur = 0;                         /* root pair */
+	unsigned long long visits = 0, tests = 0, lbtests = 0;
+	const int stride = blockDim.x;
+
+	for (;;) {
+		/* ---- interior: test both children of pair `cur` ---- */
+		while (cur >= 0) {
+			float4 q0, q1, q2, q3;
+			if (TOP_SMEM && (uint32_t)cur < sc.top_pairs) {
+				const float4 *q = s_top + 4 * cur;
+				q0 = q[0]; q1 = q[1]; q2 = q[2]; q3 = q[3];
+			} else {
+				const float4 *q = sc.pairs + 4 * (size_t)cur;
+				q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2); q3 = __ldg(q + 3);
+			}
+			if (COUNT) visits += 2;
+			const Slab L = slab_minmax(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, id);
+			const Slab R = slab_minmax(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, o, id);
+			const bool hitL = L.tmin <= L.tmax && L.tmin < limit && L.tmax > 0.0f;
+			const bool hitR = R.tmin <= R.tmax && R.tmin < limit && R.tmax > 0.0f;
+			const int refL = __float_as_int(q1.z), refR = __float_as_int(q3.z);
+			if (hitL && hitR) {
+				const bool r_first = R.tmin < L.tmin;
+				const int near = r_first ? refR : refL, far = r_first ? refL : refR;
+				const float far_t = r_first ? L.tmin : R.tmin;
+				const uint2 e = make_uint2((uint32_t)far, __float_as_uint(far_t));
+				if (sp < SMEM_STACK) s_stack[sp * stride] = e; else l_stack[sp - SMEM_STACK] = e;
+				++sp;
+				cur = near;
+			} else if (hitL) {
+				cur = refL;
+			} else if (hitR) {
+				cur = refR;
+			} else {
+				goto pop;
+			}
+		}
+		/* ---- leaf ---- */
+		{
+			const uint32_t enc = ~(uint32_t)cur;
+			const uint32_t first = enc >> 3, count = (enc & 7u) + 1u;
+			for (uint32_t k = 0; k < count; ++k) {
+				const uint32_t tri = first + k;
+				const float4 *q = sc.tris + 4 * (size_t)tri;
+				TriHit h;
+				if (COUNT) ++tests;
+				if (!triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, limit, h)) continue;
+				if (!(h.dist < best.dist || (h.dist == best.dist && tri < best.tri))) continue;
+				if (sc.verify_leafbox) {
+					const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+					if (COUNT) ++lbtests;
+					if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), o, d, max_distance)) continue;
+				}
+				best.dist = h.dist; best.tri = tri; best.s = h.s; best.t = h.t;
+				/* parameter of this hit, recovered from the distance (|P-o| = r|d| up to rounding) */
+				best_r = fminf(best_r, h.dist * inv_len);
+				limit = fminf(max_distance, best_r * 1.0001f + abs_margin);
+			}
+		}
+pop:
+		for (;;) {
+			if (sp == 0) goto done;
+			--sp;
+			const uint2 e = sp < SMEM_STACK ? s_stack[sp * stride] : l_stack[sp - SMEM_STACK];
+			if (__uint_as_float(e.y) < limit) { cur = (int)e.x; break; }
+		}
+	}
+done:
+	if (COUNT) {
+		atomicAdd(&cnt->node_visits, visits);
+		atomicAdd(&cnt->tri_tests, tests);
+		atomicAdd(&cnt->leafbox_tests, lbtests);
+	}
+}
+
+/* One ray through the right path.  Rays with a zero direction component make
+ * the reference's slab test produce 0*inf = NaN, whose "never rejects"
+ * behaviour only the literal walk reproduces. */
+template <int SMEM_STACK, bool TOP_SMEM, bool COUNT>
+RTX_DEV void closest_hit(const SceneDev &sc, const float4 *s_top, uint2 *s_stack, bool ordered_ok,
+                         f3 o, f3 d, float max_distance, HitRec &best, Counters *cnt)
+{
+	best.dist = __int_as_float(0x7f800000);
+	best.tri = 0xffffffffu;
+	best.s = best.t = 0.f;
+	const bool plain = d.x != 0.0f && d.y != 0.0f && d.z != 0.0f;   /* false for NaN too */
+	if (ordered_ok && plain) {
+		traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT>(sc, s_top, s_stack, o, d, max_distance, best, cnt);
+	} else {
+		if (COUNT) atomicAdd(&cnt->exact_rays, 1ull);
+		walk_reference<COUNT>(sc, o, d, max_distance, best, cnt);
+	}
+}
+
+/* --------------------------------------------------------------------------
+ * Pixel <-> work mapping.  The image is cut into 32x32-pixel tiles (row-major
+ * tile ids); tile t belongs to rank t % world.  A warp's unit of work is one
+ * 8x4-pixel block; 32 consecutive units cover one tile.
+ * ------------------------------------------------------------------------ */
+struct Work {
+	Camera cam;
+	uint32_t tiles_x, tiles_y;
+	uint32_t rank, world;
+	uint32_t local_tiles;        /* tiles this rank renders */
+	uint32_t num_units;          /* local_tiles * 32 */
+	unsigned int *counter;       /* persistent-kernel work counter (zeroed before launch) */
+	float *image;                /* world == 1: row-major W x H; else compact [local_tile][32][32] */
+	uint32_t *face_id;           /* optional (record mode), same indexing as image */
+	float *dist;
+	int ordered_ok;
+};
+
+RTX_DEV bool unit_pixel(const Work &w, uint32_t unit, uint32_t lane, uint32_t &x, uint32_t &y, size_t &out)
+{
+	const uint32_t ltile = unit >> 5, sub = unit & 31u;
+	const uint32_t tile = ltile * w.world + w.rank;
+	const uint32_t tx = tile % w.tiles_x, ty = tile / w.tiles_x;
+	const uint32_t px = ((sub & 3u) << 3) + (lane & 7u), py = ((sub >> 2) << 2) + (lane >> 3);
+	x = tx * RTX_TILE + px;
+	y = ty * RTX_TILE + py;
+	out = w.world > 1 ? (size_t)ltile * (RTX_TILE * RTX_TILE) + py * RTX_TILE + px : (size_t)y * w.cam.W + x;
+	return ty < w.tiles_y && x < w.cam.W && y < w.cam.H;
+}
+
+template <int SMEM_STACK, bool TOP_SMEM, bool COUNT, bool RECORD>
+RTX_DEV void trace_pixel(const SceneDev &sc, const Work &w, const float4 *s_top, uint2 *s_stack,
+                         uint32_t x, uint32_t y, size_t out, Counters *cnt)
+{
+	const f3 o = make_f3(0.0f, 0.0f, 2.0f);                           /* :284 */
+	const f3 d = primary_dir(w.cam, x, y);
+	HitRec best;
+	closest_hit<SMEM_STACK, TOP_SMEM, COUNT>(sc, s_top, s_stack, w.ordered_ok != 0, o, d, 100000.0f, best, cnt); /* :292-295 */
+	float value = 0.0f;                                               /* :297-299 */
+	if (best.tri != 0xffffffffu) value = shade_hit(sc.tnormals, best.tri, best.s, best.t, d, w.cam.shading);
+	w.image[out] = value;                                             /* :309 */
+	if (RECORD) {
+		w.face_id[out] = best.tri != 0xffffffffu ? best.tri * 3u : 0xffffffffu;
+		w.dist[out] = best.dist;
+	}
+}
+
+/* Persistent kernel: grid = SMs x resident CTAs, every warp pulls 8x4-pixel
+ * units from one atomic counter until the image is done. */
+template <int BLOCK, int MIN_BLOCKS, int SMEM_STACK, bool TOP_SMEM, bool COUNT, bool RECORD>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
+k_render_persistent(const SceneDev sc, const Work w, Counters *cnt)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint2 *s_stack_all = reinterpret_cast<uint2 *>(smem_raw);
+	float4 *s_top = reinterpret_cast<float4 *>(smem_raw + (size_t)SMEM_STACK * BLOCK * sizeof(uint2));
+	if (TOP_SMEM) {
+		for (uint32_t i = threadIdx.x; i < sc.top_pairs * 4u; i += BLOCK) s_top[i] = __ldg(sc.pairs + i);
+		__syncthreads();
+	}
+	uint2 *s_stack = s_stack_all + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31u;
+	for (;;) {
+		uint32_t unit = 0;
+		if (lane == 0) unit = atomicAdd(w.counter, 1u);
+		unit = __shfl_sync(0xffffffffu, unit, 0);
+		if (unit >= w.num_units) break;
+		uint32_t x, y;
+		size_t out;
+		if (unit_pixel(w, unit, lane, x, y, out))
+			trace_pixel<SMEM_STACK, TOP_SMEM, COUNT, RECORD>(sc, w, s_top, s_stack, x, y, out, cnt);
+		__syncwarp();
+	}
+}
+
+/* The reference's launch shape: one thread per pixel, literal walk
+ * (opencl_host.cc:145 uses 16x16 work groups; 8x4 warps of a 32x32 tile here). */
+template <bool COUNT, bool RECORD>
+__global__ void __launch_bounds__(256)
+k_render_exhaustive(const SceneDev sc, const Work w, Counters *cnt)
+{
+	const uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (unit >= w.num_units) return;
+	uint32_t x, y;
+	size_t out;
+	if (!unit_pixel(w, unit, threadIdx.x & 31u, x, y, out)) return;
+	const f3 o = make_f3(0.0f, 0.0f, 2.0f);
+	const f3 d = primary_dir(w.cam, x, y);
+	HitRec best;
+	best.dist = __int_as_float(0x7f800000); best.tri = 0xffffffffu; best.s = best.t = 0.f;
+	walk_reference<COUNT>(sc, o, d, 100000.0f, best, cnt);
+	float value = 0.0f;
+	if (best.tri != 0xffffffffu) value = shade_hit(sc.tnormals, best.tri, best.s, best.t, d, w.cam.shading);
+	w.image[out] = value;
+	if (RECORD) {
+		w.face_id[out] = best.tri != 0xffffffffu ? best.tri * 3u : 0xffffffffu;
+		w.dist[out] = best.dist;
+	}
+}
+
+/* ---------------------------- arbitrary rays ----------------------------- */
+
+struct RayWork {
+	const float4 *origins, *dirs;   /* NULL: generate (seed, first + i) */
+	uint32_t seed;
+	unsigned long long first;
+	unsigned long long nrays;
+	f3 bbmin, bbmax;
+	float max_distance;
+	unsigned int *counter;
+	uint32_t *face_id;              /* optional */
+	float *dist;                    /* optional */
+	unsigned long long *hit_count, *sum_face_id;
+	int ordered_ok;
+	int exhaustive;
+};
+
+template <int BLOCK, int MIN_BLOCKS, int SMEM_STACK, bool TOP_SMEM, bool COUNT>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
+k_trace_rays(const SceneDev sc, const RayWork w, Counters *cnt)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint2 *s_stack_all = reinterpret_cast<uint2 *>(smem_raw);
+	float4 *s_top = reinterpret_cast<float4 *>(smem_raw + (size_t)SMEM_STACK * BLOCK * sizeof(uint2));
+	if (TOP_SMEM) {
+		for (uint32_t i = threadIdx.x; i < sc.top_pairs * 4u; i += BLOCK) s_top[i] = __ldg(sc.pairs + i);
+		__syncthreads();
+	}
+	uint2 *s_stack = s_stack_all + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31u;
+	const unsigned long long nunits = (w.nrays + 31ull) >> 5;
+	unsigned long long hits = 0, idsum = 0;
+	for (;;) {
+		uint32_t unit = 0;
+		if (lane == 0) unit = atomicAdd(w.counter, 1u);
+		unit = __shfl_sync(0xffffffffu, unit, 0);
+		if (unit >= nunits) break;
+		const unsigned long long i = ((unsigned long long)unit << 5) + lane;
+		if (i < w.nrays) {
+			f3 o, d;
+			if (w.origins) {
+				const float4 oo = __ldg(w.origins + i), dd = __ldg(w.dirs + i);
+				o = make_f3(oo.x, oo.y, oo.z);
+				d = make_f3(dd.x, dd.y, dd.z);
+			} else {
+				random_ray(w.seed, w.first + i, w.bbmin, w.bbmax, o, d);
+			}
+			HitRec best;
+			closest_hit<SMEM_STACK, TOP_SMEM, COUNT>(sc, s_top, s_stack, w.ordered_ok != 0 && !w.exhaustive, o, d, w.max_distance, best, cnt);
+			const uint32_t fid = best.tri != 0xffffffffu ? best.tri * 3u : 0xffffffffu;
+			if (w.face_id) w.face_id[i] = fid;
+			if (w.dist) w.dist[i] = best.dist;
+			if (fid != 0xffffffffu) { ++hits; idsum += fid; }
+		}
+		__syncwarp();
+	}
+	if (w.hit_count) {
+		for (int s = 16; s > 0; s >>= 1) {
+			hits += __shfl_xor_sync(0xffffffffu, hits, s);
+			idsum += __shfl_xor_sync(0xffffffffu, idsum, s);
+		}
+		if (lane == 0 && hits) { atomicAdd(w.hit_count, hits); atomicAdd(w.sum_face_id, idsum); }
+	}
+}
+
+/* ------------------------------ image ops -------------------------------- */
+
+/* RayTracer::resize (src/ray_tracer.cc:3-15): n x n box sum in (ssY, ssX)
+ * order, (total / (n*n)) * 255, float -> unsigned char truncation. */
+__global__ void k_resize_u8(const float *__restrict__ img, uint32_t total_width, uint32_t width, uint32_t height,
+                            uint32_t n, unsigned char *__restrict__ out)
+{
+	const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= width || y >= height) return;
+	float total = 0.0f;
+	for (uint32_t sy = 0; sy < n; ++sy)
+		for (uint32_t sx = 0; sx < n; ++sx)
+			total = rn_add(total, img[(size_t)(y * n + sy) * total_width + (x * n + sx)]);
+	const float v = rn_mul(rn_div(total, (float)(n * n)), 255.0f);
+	out[(size_t)y * width + x] = (unsigned char)(int)v;
+}
+
+/* rank-major gathered compact tile buffers -> row-major image (rank 0) */
+__global__ void k_deinterleave(const float *__restrict__ gathered, uint32_t world, uint32_t tiles_per_rank,
+                               uint32_t tiles_x, uint32_t tiles_y, uint32_t W, uint32_t H, float *__restrict__ image)
+{
+	const uint32_t tile = blockIdx.x;
+	if (tile >= tiles_x * tiles_y) return;
+	const uint32_t rank = tile % world, ltile = tile / world;
+	const float *src = gathered + ((size_t)rank * tiles_per_rank + ltile) * (RTX_TILE * RTX_TILE);
+	const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+	for (uint32_t i = threadIdx.x; i < RTX_TILE * RTX_TILE; i += blockDim.x) {
+		const uint32_t px = i & 31u, py = i >> 5;
+		const uint32_t x = tx * RTX_TILE + px, y = ty * RTX_TILE + py;
+		if (x < W && y < H) image[(size_t)y * W + x] = src[i];
+	}
+}
+
+/* ------------------- device-side pieces of the flatten ------------------- */
+
+/* triangle records, leaf boxes and corner normals from the upload arrays */
+__global__ void k_build_triangles(const uint32_t *__restrict__ faces, const float4 *__restrict__ verts,
+                                  const float4 *__restrict__ vnormals, const uint32_t *__restrict__ leaf_node,
+                                  const float4 *__restrict__ ref_aabbs, uint32_t ntris,
+                                  float4 *__restrict__ tris, float4 *__restrict__ leafbox, float4 *__restrict__ tnormals)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= ntris) return;
+	const uint32_t i0 = faces[3 * (size_t)t], i1 = faces[3 * (size_t)t + 1], i2 = faces[3 * (size_t)t + 2];
+	const float4 A = verts[i0], B = verts[i1], C = verts[i2];
+	const f3 a = make_f3(A.x, A.y, A.z);
+	const f3 u = sub3(make_f3(B.x, B.y, B.z), a);                 /* :68 */
+	const f3 v = sub3(make_f3(C.x, C.y, C.z), a);                 /* :69 */
+	const f3 n = cross3(u, v);                                    /* :70 */
+	const float uu = dot3(u, u), uv = dot3(u, v), vv = dot3(v, v);/* :87-89 */
+	const float D = rn_sub(rn_mul(uv, uv), rn_mul(uu, vv));       /* :93 */
+	float4 *q = tris + 4 * (size_t)t;
+	q[0] = make_float4(a.x, a.y, a.z, n.x);
+	q[1] = make_float4(u.x, u.y, u.z, n.y);
+	q[2] = make_float4(v.x, v.y, v.z, n.z);
+	q[3] = make_float4(uu, uv, vv, D);
+	const uint32_t node = leaf_node[t];
+	float4 lo = ref_aabbs[2 * (size_t)node], hi = ref_aabbs[2 * (size_t)node + 1];
+	lo.w = 0.f; hi.w = 0.f;
+	leafbox[2 * (size_t)t] = lo;
+	leafbox[2 * (size_t)t + 1] = hi;
+	float4 n0 = vnormals[i0], n1 = vnormals[i1], n2 = vnormals[i2];
+	n0.w = n1.w = n2.w = 0.f;
+	tnormals[3 * (size_t)t] = n0;
+	tnormals[3 * (size_t)t + 1] = n1;
+	tnormals[3 * (size_t)t + 2] = n2;
+}

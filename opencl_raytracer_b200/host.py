@@ -1,0 +1,341 @@
+"""Python mirror of the reference's host boundary, over the C ABI (ctypes).
+
+``RayTracer`` mirrors include/ray_tracer.h:3-39 (Options, totalWidth /
+totalHeight, resize) and ``CudaHost`` mirrors ``OpenCLHost``
+(include/opencl_host.h:127-131): ``printInfo()``, ``upload(faces, nodes, aabbs,
+vertices, vnormals)``, ``__call__()`` (the reference's ``bool operator()()``)
+and ``download()``.  Every compute call goes through
+opencl_raytracer_b200/lib/librtx_b200.so (include/rtx_b200.h); there is no
+Python or CPU fallback -- a missing library or device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from .scene import Scene
+
+_LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+LIB_PATH = os.path.join(_LIBDIR, "librtx_b200.so")
+
+NO_HIT = 0xFFFFFFFF
+
+OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NOMEM = range(7)
+
+TUNE_KERNEL, TUNE_LEAF_SIZE, TUNE_RECORD_HITS, TUNE_COUNTERS, TUNE_TOP_SMEM, TUNE_BLOCKS_PER_SM, TUNE_FLATTEN_ON_DEVICE = range(1, 8)
+KERNEL_PERSISTENT, KERNEL_EXHAUSTIVE = 0, 1
+
+# every symbol include/rtx_b200.h declares (tests check the library exports them all)
+ABI_SYMBOLS = (
+    "rtx_print_info", "rtx_device_count", "rtx_device_info", "rtx_create", "rtx_upload", "rtx_render",
+    "rtx_download", "rtx_destroy", "rtx_last_error", "rtx_set_tunable", "rtx_get_stats", "rtx_render_async",
+    "rtx_synchronize", "rtx_download_hits", "rtx_download_u8", "rtx_device_image", "rtx_trace_rays",
+    "rtx_trace_rays_device", "rtx_trace_random_rays", "rtx_tile_layout", "rtx_deinterleave_async",
+)
+
+
+class RtxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("rtx error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _Options(C.Structure):
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32), ("focal_length", C.c_float), ("n_super_samples", C.c_uint32),
+        ("enable_shading", C.c_int32), ("enable_ao", C.c_int32), ("ao_max_distance", C.c_float),
+        ("ao_num_samples", C.c_uint32), ("ao_method", C.c_int32), ("ao_alpha_min", C.c_int32), ("ao_alpha_max", C.c_int32),
+        ("bvh_method", C.c_int32), ("total_width", C.c_uint32), ("total_height", C.c_uint32),
+        ("device", C.c_int32), ("jitter_seed", C.c_uint32), ("tile_rank", C.c_uint32), ("tile_world", C.c_uint32),
+    ]
+
+
+class DeviceInfo(C.Structure):
+    _fields_ = [
+        ("name", C.c_char * 256), ("cc_major", C.c_int32), ("cc_minor", C.c_int32), ("sm_count", C.c_int32),
+        ("clock_khz", C.c_int32), ("mem_clock_khz", C.c_int32), ("mem_bus_bits", C.c_int32),
+        ("global_mem_bytes", C.c_uint64), ("l2_bytes", C.c_uint64), ("smem_per_sm_bytes", C.c_uint64),
+        ("smem_per_block_optin_bytes", C.c_uint64), ("max_threads_per_sm", C.c_int32), ("regs_per_sm", C.c_int32),
+        ("driver_version", C.c_int32), ("runtime_version", C.c_int32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("rays", C.c_uint64), ("kernel_ms", C.c_double), ("kernel_launches", C.c_uint32), ("kernel_variant", C.c_uint32),
+        ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("leafbox_tests", C.c_uint64),
+        ("exact_path_rays", C.c_uint64), ("tree_depth", C.c_uint32), ("num_pairs", C.c_uint32),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the C-ABI library and declare its prototypes.  Raises ImportError when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, u32p, fp = C.c_void_p, C.c_void_p, C.c_void_p
+    lib.rtx_print_info.restype = C.c_int
+    lib.rtx_device_count.restype = C.c_int
+    lib.rtx_device_count.argtypes = [C.POINTER(C.c_int)]
+    lib.rtx_device_info.restype = C.c_int
+    lib.rtx_device_info.argtypes = [C.c_int, C.POINTER(DeviceInfo)]
+    lib.rtx_create.restype = C.c_int
+    lib.rtx_create.argtypes = [C.POINTER(vp), C.POINTER(_Options)]
+    lib.rtx_upload.restype = C.c_int
+    lib.rtx_upload.argtypes = [vp, u32p, C.c_size_t, u32p, C.c_size_t, fp, C.c_size_t, fp, C.c_size_t, fp, C.c_size_t]
+    lib.rtx_render.restype = C.c_int
+    lib.rtx_render.argtypes = [vp]
+    lib.rtx_download.restype = C.c_int
+    lib.rtx_download.argtypes = [vp, fp]
+    lib.rtx_destroy.restype = None
+    lib.rtx_destroy.argtypes = [vp]
+    lib.rtx_last_error.restype = C.c_char_p
+    lib.rtx_last_error.argtypes = [vp]
+    lib.rtx_set_tunable.restype = C.c_int
+    lib.rtx_set_tunable.argtypes = [vp, C.c_int, C.c_int64]
+    lib.rtx_get_stats.restype = C.c_int
+    lib.rtx_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.rtx_render_async.restype = C.c_int
+    lib.rtx_render_async.argtypes = [vp, vp]
+    lib.rtx_synchronize.restype = C.c_int
+    lib.rtx_synchronize.argtypes = [vp]
+    lib.rtx_download_hits.restype = C.c_int
+    lib.rtx_download_hits.argtypes = [vp, u32p, fp]
+    lib.rtx_download_u8.restype = C.c_int
+    lib.rtx_download_u8.argtypes = [vp, vp]
+    lib.rtx_device_image.restype = C.c_int
+    lib.rtx_device_image.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.rtx_trace_rays.restype = C.c_int
+    lib.rtx_trace_rays.argtypes = [vp, fp, fp, C.c_size_t, C.c_float, u32p, fp]
+    lib.rtx_trace_rays_device.restype = C.c_int
+    lib.rtx_trace_rays_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_float, vp, vp, vp]
+    lib.rtx_trace_random_rays.restype = C.c_int
+    lib.rtx_trace_random_rays.argtypes = [vp, C.c_uint32, C.c_uint64, C.c_size_t, C.c_float, u32p, fp,
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.rtx_tile_layout.restype = C.c_int
+    lib.rtx_tile_layout.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.rtx_deinterleave_async.restype = C.c_int
+    lib.rtx_deinterleave_async.argtypes = [vp, vp, C.c_uint32, vp]
+    _lib = lib
+    return lib
+
+
+def _check(lib, ctx, rc):
+    if rc != OK:
+        msg = lib.rtx_last_error(ctx)
+        raise RtxError(rc, msg.decode() if msg else "?")
+
+
+def device_count() -> int:
+    lib = load_library()
+    n = C.c_int(0)
+    rc = lib.rtx_device_count(C.byref(n))
+    if rc not in (OK, ERR_NO_DEVICE):
+        _check(lib, None, rc)
+    return n.value
+
+
+def device_info(device: int = 0) -> DeviceInfo:
+    lib = load_library()
+    info = DeviceInfo()
+    _check(lib, None, lib.rtx_device_info(device, C.byref(info)))
+    return info
+
+
+def tile_layout(total_width: int, total_height: int, world: int):
+    lib = load_library()
+    tx, ty, tpr = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib.rtx_tile_layout(total_width, total_height, world, C.byref(tx), C.byref(ty), C.byref(tpr))
+    return tx.value, ty.value, tpr.value
+
+
+@dataclass
+class Options:
+    """RayTracer::Options (include/ray_tracer.h:17-30) with render.cc:17's defaults, AO off."""
+    width: int = 600
+    height: int = 600
+    focalLength: float = 1.0
+    nSuperSamples: int = 4
+    enableShading: bool = True
+    enableAO: bool = False
+    aoMaxDistance: float = 0.2
+    aoNumSamples: int = 0
+    aoMethod: int = 0
+    aoAlphaMin: int = 4
+    aoAlphaMax: int = 90
+    bvhMethod: int = 0
+
+
+class RayTracer:
+    """include/ray_tracer.h:31-38."""
+
+    def __init__(self, options: Options):
+        self.options = options
+        n = int(math.sqrt(options.nSuperSamples))   # (unsigned int) sqrt(nSuperSamples)
+        self.totalWidth = options.width * n
+        self.totalHeight = options.height * n
+
+    @property
+    def n(self) -> int:
+        return int(math.sqrt(self.options.nSuperSamples))
+
+
+class CudaHost:
+    """Drop-in for ``OpenCLHost`` (include/opencl_host.h:127-131)."""
+
+    def __init__(self, rt: RayTracer, device: int = 0, jitter_seed: int = 0, tile_rank: int = 0, tile_world: int = 1):
+        self._lib = load_library()
+        self.rt = rt
+        o = rt.options
+        self._opt = _Options(o.width, o.height, o.focalLength, o.nSuperSamples, int(o.enableShading), int(o.enableAO),
+                             o.aoMaxDistance, o.aoNumSamples, o.aoMethod, o.aoAlphaMin, o.aoAlphaMax, o.bvhMethod,
+                             rt.totalWidth, rt.totalHeight, device, jitter_seed, tile_rank, tile_world)
+        self._ctx = C.c_void_p()
+        _check(self._lib, None, self._lib.rtx_create(C.byref(self._ctx), C.byref(self._opt)))
+        self.tile_world = max(1, tile_world)
+        self.tile_rank = tile_rank if tile_world > 1 else 0
+
+    # -- lifetime --
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.rtx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        _check(self._lib, self._ctx, rc)
+
+    # -- the reference's surface --
+    @staticmethod
+    def printInfo():
+        return load_library().rtx_print_info()
+
+    def upload(self, faces, nodes, aabbs, vertices, vnormals):
+        faces = np.ascontiguousarray(faces, np.uint32)
+        nodes = np.ascontiguousarray(nodes, np.uint32)
+        aabbs = np.ascontiguousarray(aabbs, np.float32)
+        vertices = np.ascontiguousarray(vertices, np.float32)
+        vnormals = np.ascontiguousarray(vnormals, np.float32)
+        self._ck(self._lib.rtx_upload(self._ctx, faces.ctypes.data, faces.size, nodes.ctypes.data, nodes.size,
+                                      aabbs.ctypes.data, aabbs.size // 4, vertices.ctypes.data, vertices.size // 4,
+                                      vnormals.ctypes.data, vnormals.size // 4))
+
+    def upload_scene(self, scene: Scene):
+        self.upload(scene.faces, scene.nodes, scene.aabbs, scene.vertices, scene.normals)
+
+    def __call__(self) -> bool:
+        self._ck(self._lib.rtx_render(self._ctx))
+        return True
+
+    def download(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.rt.totalHeight, self.rt.totalWidth), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.rt.totalWidth * self.rt.totalHeight
+        self._ck(self._lib.rtx_download(self._ctx, out.ctypes.data))
+        return out
+
+    # -- extensions --
+    def set_tunable(self, which: int, value: int):
+        self._ck(self._lib.rtx_set_tunable(self._ctx, which, value))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self._lib.rtx_get_stats(self._ctx, C.byref(s)))
+        return s.as_dict()
+
+    def render_async(self, stream: int = 0):
+        self._ck(self._lib.rtx_render_async(self._ctx, C.c_void_p(stream)))
+
+    def synchronize(self):
+        self._ck(self._lib.rtx_synchronize(self._ctx))
+
+    def download_hits(self):
+        n = (self.rt.totalHeight, self.rt.totalWidth)
+        fid = np.empty(n, np.uint32)
+        dist = np.empty(n, np.float32)
+        self._ck(self._lib.rtx_download_hits(self._ctx, fid.ctypes.data, dist.ctypes.data))
+        return fid, dist
+
+    def download_u8(self) -> np.ndarray:
+        out = np.empty((self.rt.options.height, self.rt.options.width), np.uint8)
+        self._ck(self._lib.rtx_download_u8(self._ctx, out.ctypes.data))
+        return out
+
+    def device_image(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.rtx_device_image(self._ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def trace_rays(self, origins, dirs, max_distance: float = 100000.0):
+        origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 4)
+        dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 4)
+        n = origins.shape[0]
+        fid = np.empty(n, np.uint32)
+        dist = np.empty(n, np.float32)
+        self._ck(self._lib.rtx_trace_rays(self._ctx, origins.ctypes.data, dirs.ctypes.data, n, C.c_float(max_distance),
+                                          fid.ctypes.data, dist.ctypes.data))
+        return fid, dist
+
+    def trace_rays_device(self, d_origins: int, d_dirs: int, nrays: int, max_distance: float, d_face_id: int, d_distance: int, stream: int = 0):
+        self._ck(self._lib.rtx_trace_rays_device(self._ctx, C.c_void_p(d_origins), C.c_void_p(d_dirs), nrays,
+                                                 C.c_float(max_distance), C.c_void_p(d_face_id), C.c_void_p(d_distance),
+                                                 C.c_void_p(stream)))
+
+    def trace_random_rays(self, seed: int, first: int, nrays: int, max_distance: float = 100000.0, want_arrays: bool = False):
+        fid = np.empty(nrays, np.uint32) if want_arrays else None
+        dist = np.empty(nrays, np.float32) if want_arrays else None
+        hits, idsum = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.rtx_trace_random_rays(self._ctx, seed, first, nrays, C.c_float(max_distance),
+                                                 fid.ctypes.data if want_arrays else None,
+                                                 dist.ctypes.data if want_arrays else None,
+                                                 C.byref(hits), C.byref(idsum)))
+        return hits.value, idsum.value, fid, dist
+
+    def deinterleave_async(self, d_gathered: int, world: int, stream: int = 0):
+        self._ck(self._lib.rtx_deinterleave_async(self._ctx, C.c_void_p(d_gathered), world, C.c_void_p(stream)))
+
+
+def write_pgm(path: str, image_u8: np.ndarray) -> None:
+    """src/render.cc:130-137: "P5 <w> <h> 255\\n" + raw bytes."""
+    h, w = image_u8.shape
+    with open(path, "wb") as f:
+        f.write(b"P5 %d %d 255\n" % (w, h))
+        f.write(np.ascontiguousarray(image_u8, np.uint8).tobytes())
+
+
+def host_resize(tmp: np.ndarray, rt: RayTracer) -> np.ndarray:
+    """RayTracer::resize (src/ray_tracer.cc:3-15) on the host, vectorised with
+    the same summation order: ssY outer, ssX inner, float32 accumulation."""
+    n = rt.n
+    h, w = rt.options.height, rt.options.width
+    t = np.ascontiguousarray(tmp, np.float32).reshape(rt.totalHeight, rt.totalWidth)
+    total = np.zeros((h, w), np.float32)
+    for sy in range(n):
+        for sx in range(n):
+            total = (total + t[sy:h * n:n, sx:w * n:n]).astype(np.float32)
+    v = (total / np.float32(n * n)).astype(np.float32) * np.float32(255)
+    return v.astype(np.float32).astype(np.int32).astype(np.uint8)
