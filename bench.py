@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s closest-hit on the sibenik stand-in at 4K (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1]
+
+Workload (default, all N): config C3 -- sibenik stand-in (75 256 triangles), `render -a 0 -w 3840 -h 2160
+-s 16` => 15360 x 8640 = 132 710 400 primary rays per frame on the reference's regular 4x4 sample grid,
+image tile-partitioned over the N GPUs (strong scaling), one NCCL gather to rank 0 per frame.
+A "step" = one frame: traversal kernel on every rank (+ gather + de-interleave when N > 1).
+
+  value      rays of the frame / device time of the step (CUDA events on the launching stream, max over
+             ranks), scene resident in HBM.
+  e2e        the same frame through the reference's five calls on HOST buffers (rtx_upload of the five
+             reference arrays -> rtx_render -> rtx_download of the float image), copies inside the timed
+             region; e2e_u8 is the opt-in variant that resizes on the device and downloads bytes.
+  roofline   algorithmic bytes (B = 32 V + 48 T + 48 h + 4 per ray, V/T/h counted by the oracle
+             under the reference's exhaustive walk) x rays / kernel time, against the measured HBM peak.
+             The scene (11 MB) lives in L2/L1, so `frac` may exceed 1: the cache-level numbers that
+             actually bound the kernel are in roofline.l2 (measured L2 peak from rtx_probe_bandwidth).
+  cpu_baseline  the reference's own kernel text (oracle/_ref) -- or the C port when it is absent -- on the
+             box's host cores, on a bounded row sample of the same frame.
+
+--impl reference runs only that CPU arm (rank 0) with the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, nSuperSamples, scene, description)
+    "c3": (3840, 2160, 16, "sibenik", "C3 sibenik-standin 3840x2160 s=16 (15360x8640 = 132.7M rays, regular grid)"),
+    "c2": (1920, 1080, 4, "sibenik", "C2 sibenik-standin 1920x1080 s=4 (3840x2160 = 8.29M rays)"),
+    "c1": (600, 600, 4, "bunny", "C1 bunny 600x600 s=4 (1200x1200 = 1.44M rays)"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_scene(kind):
+    from opencl_raytracer_b200 import scene, scenes
+    if kind == "bunny":
+        from oracle import pyoracle as po          # only for the staged reference mesh file
+        v, f = po.read_mesh_bin(po.staged_bunny_path())
+        return scene.scene_from_mesh(v, f, name="bunny")
+    v, f = scenes.sibenik_standin()
+    return scene.scene_from_mesh(v, f, name="sibenik_standin")
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of one GPU, sampled every 50 ms during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+class CpuArm:
+    """The reference CPU path on a bounded row sample of the frame: the reference's own kernel text
+    (oracle/_ref, kind "reference") when it was compiled in the build container, else the C port."""
+
+    def __init__(self, sc, tw, th, budget_s=12.0):
+        from oracle import pyoracle as po
+        self.po, self.sc, self.tw, self.th = po, sc, tw, th
+        self.use_ref = po.ref() is not None
+        self.cores = int(po.ref().ref_online_cpus() if self.use_ref else po.port().orc_online_cpus())
+        step = max(1, th // 16)
+        self.rows = (step // 2, th, step)
+        self.run()                                       # warm-up: page in, start threads
+        dt = self.run()
+        rate = self.nrays / dt
+        want_rows = int(min(th, max(len(range(*self.rows)), rate * budget_s / tw)))
+        step = max(1, th // want_rows)
+        self.rows = (step // 2, th, step)
+
+    @property
+    def nrays(self):
+        return len(range(*self.rows)) * self.tw
+
+    def run(self):
+        t = time.perf_counter()
+        if self.use_ref:
+            self.po.ref_render(self.sc, self.tw, self.th, 1.0, True, rows=self.rows)
+        else:
+            self.po.render(self.sc, self.tw, self.th, 1.0, True, rows=self.rows, want_ids=False)
+        return time.perf_counter() - t
+
+    def info(self, mrays, dt):
+        return {"value": mrays, "unit": "Mrays/s", "cores": self.cores, "kind": "reference" if self.use_ref else "port",
+                "sample": "every %d-th row of the %dx%d frame (%d rows, %.2fM rays, %.2f s per pass), %d pinned threads"
+                          % (self.rows[2], self.tw, self.th, len(range(*self.rows)), self.nrays / 1e6, dt, self.cores)}
+
+
+def oracle_counters(sc, tw, th):
+    """V, T, h of the frame under the reference's exhaustive walk, from a row sample (oracle counting mode)."""
+    from oracle import pyoracle as po
+    step = max(1, th // 64)
+    r = po.render(sc, tw, th, 1.0, True, rows=(step // 2, th, step), want_ids=False, want_counters=True)
+    c = r.counters
+    return c["V"], c["T"], c["h"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    width, height, nss, scene_kind, desc = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import __graft_entry__ as g
+        g.build(quiet=True)
+        sc = build_scene(scene_kind)
+        n = int(np.sqrt(nss))
+        tw, th = width * n, height * n
+        arm = CpuArm(sc, tw, th, budget_s=3.0)
+        times = []
+        for i in range(args.warmup + args.steps):
+            dt = arm.run()
+            if i >= args.warmup:
+                times.append(dt)
+        v = arm.nrays * len(times) / sum(times) / 1e6
+        info = arm.info(v, float(np.mean(times)))
+        rays_per_step = arm.nrays
+        print(json.dumps({
+            "impl": "reference", "metric": "Mrays/s closest-hit (sibenik, 4K)", "value": v, "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": rays_per_step / v / 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "scene": sc.name, "triangles": sc.num_triangles, "parallelism": "host threads"},
+            "cpu_baseline": info,
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from opencl_raytracer_b200 import host, multigpu
+    import __graft_entry__ as g
+
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        g.build(quiet=True)
+    if world > 1:
+        dist.barrier()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    sc = build_scene(scene_kind)
+    rt = host.RayTracer(host.Options(width=width, height=height, nSuperSamples=nss))
+    tw, th = rt.totalWidth, rt.totalHeight
+    rays = tw * th
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---------------- value: scene resident, device-timed ----------------
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)                       # kernels, NCCL gather and the events all use this stream
+    r = multigpu.TiledRenderer(rt, sc, rank, world, local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    for _ in range(args.warmup):
+        r.render_frame()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = r.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (not timed)
+        if world > 1:
+            dist.barrier()
+        ev[k][0].record()
+        r.render_frame()
+        ev[k][1].record()
+        torch.cuda.synchronize(dev)
+        kernel_ms.append(r.host.stats()["kernel_ms"])
+    barrier()
+    clocks = sampler.result()
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)   # max over ranks, per step
+    step_ms = step_ms.cpu().numpy()
+    total_ms = float(step_ms.sum())
+    launches = r.kernel_launches - launches0
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    km = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(lt)
+        dist.all_reduce(km, op=dist.ReduceOp.MAX)
+    value = rays * args.steps / (total_ms * 1e-3) / 1e6
+    kernel_ms_mean = float(km.item())
+
+    # parity spot check inside the bench (rank 0): sampled rows of the gathered frame == oracle
+    parity = None
+    if rank == 0:
+        from oracle import pyoracle as po
+        img = r.download()
+        step = max(1, th // 24)
+        rows = (step // 3, th, step)
+        ref = po.render(sc, tw, th, 1.0, True, rows=rows, want_ids=False)
+        sel = slice(*rows)
+        parity = {"rows_checked": len(range(*rows)), "pixels_differing": int((img[sel] != ref.image[sel]).sum())}
+        del img
+
+    # ---------------- e2e: the reference's five calls on host buffers ----------------
+    e2e = e2e_u8 = None
+    if not args.no_e2e:
+        arrs = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (sc.faces, sc.nodes, sc.aabbs, sc.vertices, sc.normals)]
+        np_arrs = [a.numpy() for a in arrs]
+        h2d = int(sum(a.numel() * a.element_size() for a in arrs))
+        out_f = torch.empty((th, tw), dtype=torch.float32).pin_memory().numpy() if rank == 0 else None
+        hr = r.host
+
+        phase = {}
+
+        def timed(name, fn):
+            t0 = time.perf_counter()
+            out = fn()
+            phase[name] = phase.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+            return out
+
+        def render_sync():
+            r.render_frame()
+            torch.cuda.synchronize(dev)
+
+        def frame_float():
+            timed("upload", lambda: hr.upload(*np_arrs))
+            timed("render", render_sync)
+            if rank == 0:
+                timed("download", lambda: hr.download(out_f))
+
+        def frame_u8():
+            timed("upload", lambda: hr.upload(*np_arrs))
+            timed("render", render_sync)
+            if rank == 0:
+                timed("download", lambda: hr.download_u8())
+
+        res, phases = [], []
+        for fn in (frame_float, frame_u8):
+            for _ in range(2):
+                fn()
+            barrier()
+            phase.clear()
+            t0 = time.perf_counter()
+            nst = max(3, args.steps // 2)
+            for _ in range(nst):
+                fn()
+                if world > 1:
+                    dist.barrier()
+            torch.cuda.synchronize(dev)
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            res.append(rays * nst / float(dt.item()) / 1e6)
+            phases.append({k: v / nst for k, v in phase.items()})
+        e2e = {"value": res[0], "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": rays * 4,
+               "calls": "rtx_upload + rtx_render(+gather) + rtx_download(float image), pinned host buffers, wall clock",
+               "phase_ms": phases[0]}
+        e2e_u8 = {"value": res[1], "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": width * height,
+                  "calls": "rtx_upload + rtx_render(+gather) + rtx_download_u8 (device resize, ray_tracer.cc:3-15 order)",
+                  "phase_ms": phases[1]}
+
+    # ---------------- roofline + cpu baseline (rank 0, N = 1 only for the CPU leg) ----------------
+    roofline = cpu = None
+    if rank == 0:
+        V, T, hfrac = oracle_counters(sc, tw, th)
+        B = 32.0 * V + 48.0 * T + 48.0 * hfrac + 4.0
+        peak, peak_src = load_peaks()
+        k_rays = rays / world if world > 1 else rays
+        achieved = B * k_rays / (kernel_ms_mean * 1e-3) / 1e9
+        l2_peak = r.host.probe_bandwidth(0, 32 << 20, 20)
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "kernel": "k_render_persistent", "kernel_ms": kernel_ms_mean,
+                    "algorithmic_bytes_per_ray": B, "V": V, "T": T, "h": hfrac,
+                    "note": "scene is L2/L1-resident: compulsory HBM traffic is the 4 B/ray image write; "
+                            "algorithmic bytes follow the reference's exhaustive walk, the kernel culls",
+                    "l2": {"achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
+                           "peak_source": "rtx_probe_bandwidth: ld.cg float4 sweep of a 32 MiB buffer, this run"}}
+        if world == 1 and not args.no_cpu:
+            arm = CpuArm(sc, tw, th, budget_s=12.0)
+            dt = arm.run()
+            cpu = arm.info(arm.nrays / dt / 1e6, dt)
+    r.close()
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Mrays/s closest-hit (sibenik, 4K)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "scene": sc.name, "triangles": sc.num_triangles, "rays_per_step": rays,
+                       "parallelism": "interleaved 32x32 tiles over %d GPU(s), scene replicated, 1 NCCL gather/frame" % world,
+                       "l2": "flushed between timed iterations (256 MiB memset, untimed)"},
+            "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(lt.item()),
+            "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity,
+            "step_ms": [float(x) for x in step_ms],
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

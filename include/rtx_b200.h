@@ -145,8 +145,10 @@ const char *rtx_last_error(const rtx_ctx *ctx);
 int rtx_set_tunable(rtx_ctx *ctx, int which, int64_t value);
 int rtx_get_stats(const rtx_ctx *ctx, rtx_stats *stats);
 
-/* Enqueue the render on a CUDA stream (cudaStream_t as void*; NULL = the
- * context's own stream) without waiting. */
+/* Enqueue the render on the caller's CUDA stream (cudaStream_t as void*; NULL
+ * is CUDA's legacy default stream) without waiting.  The blocking calls use a
+ * private non-blocking stream of the context; rtx_synchronize waits for the
+ * whole device. */
 int rtx_render_async(rtx_ctx *ctx, void *stream);
 int rtx_synchronize(rtx_ctx *ctx);
 
@@ -165,6 +167,11 @@ int rtx_download_u8(rtx_ctx *ctx, unsigned char *image);
  * number of floats. */
 int rtx_device_image(rtx_ctx *ctx, void **device_ptr, size_t *count);
 
+/* Render into caller-owned device memory (e.g. a torch tensor that NCCL will
+ * gather) instead of the context's own buffer: `count` floats, at least what
+ * rtx_device_image reports.  device_ptr == NULL restores the internal buffer. */
+int rtx_bind_output(rtx_ctx *ctx, void *device_ptr, size_t count);
+
 /* Closest hit for arbitrary rays (config C5), reference scene_intersect
  * semantics with the given max_distance.  origins/dirs: 4 floats per ray.
  * Host-pointer and device-pointer forms. */
@@ -177,6 +184,12 @@ int rtx_trace_rays_device(rtx_ctx *ctx, const void *d_origins, const void *d_dir
  * are given (either may be NULL).  sum_face_id / hit_count: checksums. */
 int rtx_trace_random_rays(rtx_ctx *ctx, uint32_t seed, uint64_t first, size_t nrays, float max_distance,
                           uint32_t *face_id, float *distance, uint64_t *hit_count, uint64_t *sum_face_id);
+
+/* Cache bandwidth probe for the roofline denominators of cache-resident scenes
+ * (MEASURED_PEAKS.json only holds HBM): 128-bit loads over a scratch buffer of
+ * `bytes`, `iters` sweeps.  level 0: whole buffer from every CTA, L1 bypassed
+ * (L2 when bytes fits L2, HBM when not); level 1: 64 KB per CTA through L1. */
+int rtx_probe_bandwidth(rtx_ctx *ctx, int level, size_t bytes, int iters, double *gbps);
 
 /* ---- multi-GPU tile partition (one context per rank) ---- */
 

@@ -74,6 +74,7 @@ struct rtx_ctx {
 	/* image */
 	uint32_t W = 0, H = 0, tiles_x = 0, tiles_y = 0, tiles_per_rank = 0, local_tiles = 0;
 	uint32_t rank = 0, world = 1;
+	float *ext_image = nullptr;  /* caller-owned output (rtx_bind_output) */
 	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums;
 	bool rendered = false, full_valid = false;
 	/* stats */
@@ -562,7 +563,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	w.local_tiles = c->local_tiles;
 	w.num_units = c->local_tiles * 32u;
 	w.counter = c->d_counter.as<unsigned int>();
-	w.image = c->d_image.as<float>();
+	w.image = c->ext_image ? c->ext_image : c->d_image.as<float>();
 	w.face_id = c->record_hits ? c->d_face_id.as<uint32_t>() : nullptr;
 	w.dist = c->record_hits ? c->d_dist.as<float>() : nullptr;
 	w.ordered_ok = c->tree_depth <= RTX_STACK_MAX ? 1 : 0;
@@ -583,7 +584,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 
 int rtx_render_async(rtx_ctx *c, void *stream)
 {
-	return enqueue_render(c, stream ? static_cast<cudaStream_t>(stream) : (c ? c->stream : nullptr));
+	return enqueue_render(c, static_cast<cudaStream_t>(stream));
 }
 
 int rtx_synchronize(rtx_ctx *c)
@@ -619,14 +620,24 @@ int rtx_device_image(rtx_ctx *c, void **device_ptr, size_t *count)
 		if (count) *count = (size_t)c->W * c->H;
 		return RTX_OK;
 	}
-	*device_ptr = c->d_image.p;
+	*device_ptr = c->ext_image ? (void *)c->ext_image : c->d_image.p;
 	if (count) *count = c->world > 1 ? (size_t)c->tiles_per_rank * RTX_TILE * RTX_TILE : (size_t)c->W * c->H;
+	return RTX_OK;
+}
+
+int rtx_bind_output(rtx_ctx *c, void *device_ptr, size_t count)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	const size_t need = c->world > 1 ? (size_t)c->tiles_per_rank * RTX_TILE * RTX_TILE : (size_t)c->W * c->H;
+	if (device_ptr && count < need) return fail(c, RTX_ERR_ARG, "bound output is smaller than this context's share of the image");
+	c->ext_image = static_cast<float *>(device_ptr);
+	c->rendered = false;
 	return RTX_OK;
 }
 
 static const float *full_image(rtx_ctx *c)
 {
-	if (c->world == 1) return c->d_image.as<float>();
+	if (c->world == 1) return c->ext_image ? c->ext_image : c->d_image.as<float>();
 	return c->full_valid ? c->d_image_full.as<float>() : nullptr;
 }
 
@@ -680,7 +691,7 @@ int rtx_deinterleave_async(rtx_ctx *c, const void *d_gathered, uint32_t world, v
 	CU(c, c->d_image_full.alloc((size_t)c->W * c->H * sizeof(float)));
 	uint32_t tx, ty, tpr;
 	rtx_tile_layout(c->W, c->H, world, &tx, &ty, &tpr);
-	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	k_deinterleave<<<tx * ty, 256, 0, st>>>(static_cast<const float *>(d_gathered), world, tpr, tx, ty, c->W, c->H,
 	                                         c->d_image_full.as<float>());
 	CU(c, cudaGetLastError());
@@ -697,7 +708,7 @@ int rtx_trace_rays_device(rtx_ctx *c, const void *d_origins, const void *d_dirs,
 	if (!d_origins || !d_dirs) return fail(c, RTX_ERR_ARG, "null ray arrays");
 	if (nrays >= (1ull << 36)) return fail(c, RTX_ERR_ARG, "too many rays in one call");
 	CU(c, cudaSetDevice(c->device));
-	cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	RayWork w{};
 	w.origins = static_cast<const float4 *>(d_origins);
 	w.dirs = static_cast<const float4 *>(d_dirs);
@@ -742,7 +753,7 @@ int rtx_trace_rays(rtx_ctx *c, const float *origins, const float *dirs, size_t n
 		cleanup();
 		return cuda_fail(c, e, "cudaMemcpy(rays)");
 	}
-	rc = rtx_trace_rays_device(c, d_o.p, d_d.p, nrays, max_distance, d_f.p, d_t.p, nullptr);
+	rc = rtx_trace_rays_device(c, d_o.p, d_d.p, nrays, max_distance, d_f.p, d_t.p, c->stream);
 	if (rc == RTX_OK) {
 		if (face_id && (e = cudaMemcpyAsync(face_id, d_f.p, nrays * 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) rc = cuda_fail(c, e, "cudaMemcpy(face_id)");
 		if (rc == RTX_OK && distance && (e = cudaMemcpyAsync(distance, d_t.p, nrays * 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) rc = cuda_fail(c, e, "cudaMemcpy(distance)");
@@ -800,6 +811,35 @@ int rtx_trace_random_rays(rtx_ctx *c, uint32_t seed, uint64_t first, size_t nray
 	c->stats.kernel_variant = (w.exhaustive || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
 	c->rendered = false;
 	return finish_stats(c);
+}
+
+/* level 0 = L2 (or HBM when bytes exceeds L2), level 1 = L1 (per-CTA 64 KB slices). */
+int rtx_probe_bandwidth(rtx_ctx *c, int level, size_t bytes, int iters, double *gbps)
+{
+	if (!c || !gbps || iters < 1 || bytes < (1u << 20)) return fail(c, RTX_ERR_ARG, "bad probe arguments");
+	CU(c, cudaSetDevice(c->device));
+	DevBuf buf, sink;
+	cudaError_t e;
+	if ((e = buf.alloc(bytes)) != cudaSuccess || (e = sink.alloc(16)) != cudaSuccess) { buf.release(); return cuda_fail(c, e, "cudaMalloc(probe)"); }
+	cudaMemsetAsync(buf.p, 0, bytes, c->stream);
+	const size_t n_vecs = bytes / 16, per_cta = level == 1 ? (64u << 10) / 16 : 0;
+	const unsigned grid = (unsigned)c->sm_count * 4;
+	float best = 1e30f;
+	for (int rep = 0; rep < 4; ++rep) {      /* rep 0 warms the cache */
+		cudaEventRecord(c->ev0, c->stream);
+		k_probe_bw<<<grid, 512, 0, c->stream>>>(buf.as<float4>(), n_vecs, iters, per_cta, sink.as<float>());
+		cudaEventRecord(c->ev1, c->stream);
+		if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { buf.release(); sink.release(); return cuda_fail(c, e, "probe kernel"); }
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+		if (rep > 0 && ms < best) best = ms;
+	}
+	const double moved = level == 1 ? (double)grid * per_cta * 16.0 * iters : (double)n_vecs * 16.0 * iters;
+	*gbps = moved / (best * 1e-3) / 1e9;
+	buf.release();
+	sink.release();
+	c->ev_pending = false;
+	return RTX_OK;
 }
 
 } /* extern "C" */

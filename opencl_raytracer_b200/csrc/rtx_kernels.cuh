@@ -123,7 +123,11 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ s_t
 	const float inv_len = rsqrtf(fmaxf(d.x * d.x + d.y * d.y + d.z * d.z, 1e-30f));
 	const float scale = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), sc.scene_scale));
 	const float abs_margin = 1e-5f * scale * inv_len;
-	float limit = max_distance;          /* boxes/triangles entering beyond this cannot win */
+	/* `cull`: ray parameter beyond which nothing can beat the best hit so far.  Boxes also obey the
+	 * reference's max_distance (intersect_kernel.cl:60); triangles do not -- the reference accepts a
+	 * hit at any distance once its leaf box passed. */
+	float cull = __int_as_float(0x7f800000);
+	float limit = max_distance;          /* = min(max_distance, cull), for boxes */
 	float best_r = __int_as_float(0x7f800000);
 	uint2 l_stack[RTX_STACK_MAX - SMEM_STACK];
 	int sp = 0;
@@ -173,7 +177,7 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ s_t
 				const float4 *q = sc.tris + 4 * (size_t)tri;
 				TriHit h;
 				if (COUNT) ++tests;
-				if (!triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, limit, h)) continue;
+				if (!triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, cull, h)) continue;
 				if (!(h.dist < best.dist || (h.dist == best.dist && tri < best.tri))) continue;
 				if (sc.verify_leafbox) {
 					const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
@@ -183,7 +187,8 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ s_t
 				best.dist = h.dist; best.tri = tri; best.s = h.s; best.t = h.t;
 				/* parameter of this hit, recovered from the distance (|P-o| = r|d| up to rounding) */
 				best_r = fminf(best_r, h.dist * inv_len);
-				limit = fminf(max_distance, best_r * 1.0001f + abs_margin);
+				cull = best_r * 1.0001f + abs_margin;
+				limit = fminf(max_distance, cull);
 			}
 		}
 pop:
@@ -452,4 +457,39 @@ __global__ void k_build_triangles(const uint32_t *__restrict__ faces, const floa
 	tnormals[3 * (size_t)t] = n0;
 	tnormals[3 * (size_t)t + 1] = n1;
 	tnormals[3 * (size_t)t + 2] = n2;
+}
+
+/* ------------------------- cache bandwidth probe ------------------------- */
+
+/* Streams a buffer with 128-bit loads; the roofline denominators for scenes
+ * that live in L2/L1 come from here (MEASURED_PEAKS.json only has HBM).
+ * per_cta_vecs == 0: every CTA sweeps the whole buffer, L1 bypassed (ld.cg):
+ * L2 bandwidth when the buffer fits L2, HBM when it does not.
+ * per_cta_vecs  > 0: each CTA re-reads its own slice through L1 (ld.ca). */
+__global__ void __launch_bounds__(512)
+k_probe_bw(const float4 *__restrict__ buf, size_t n_vecs, int iters, size_t per_cta_vecs, float *__restrict__ sink)
+{
+	float acc = 0.f;
+	if (per_cta_vecs == 0) {
+		const size_t stride = (size_t)gridDim.x * blockDim.x;
+		for (int it = 0; it < iters; ++it) {
+			size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+			for (; i + 3 * stride < n_vecs; i += 4 * stride) {
+				const float4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c = __ldcg(buf + i + 2 * stride), d = __ldcg(buf + i + 3 * stride);
+				acc += a.x + b.y + c.z + d.w;
+			}
+			for (; i < n_vecs; i += stride) acc += __ldcg(buf + i).x;
+		}
+	} else {
+		const float4 *mine = buf + ((size_t)blockIdx.x * per_cta_vecs) % (n_vecs - per_cta_vecs + 1);
+		for (int it = 0; it < iters; ++it) {
+			size_t i = threadIdx.x;
+			for (; i + 3 * blockDim.x < per_cta_vecs; i += 4 * blockDim.x) {
+				const float4 a = __ldca(mine + i), b = __ldca(mine + i + blockDim.x), c = __ldca(mine + i + 2 * blockDim.x), d = __ldca(mine + i + 3 * blockDim.x);
+				acc += a.x + b.y + c.z + d.w;
+			}
+			for (; i < per_cta_vecs; i += blockDim.x) acc += __ldca(mine + i).x;
+		}
+	}
+	if (acc == 12345.678f) *sink = acc;
 }

@@ -34,7 +34,8 @@ ABI_SYMBOLS = (
     "rtx_print_info", "rtx_device_count", "rtx_device_info", "rtx_create", "rtx_upload", "rtx_render",
     "rtx_download", "rtx_destroy", "rtx_last_error", "rtx_set_tunable", "rtx_get_stats", "rtx_render_async",
     "rtx_synchronize", "rtx_download_hits", "rtx_download_u8", "rtx_device_image", "rtx_trace_rays",
-    "rtx_trace_rays_device", "rtx_trace_random_rays", "rtx_tile_layout", "rtx_deinterleave_async",
+    "rtx_trace_rays_device", "rtx_trace_random_rays", "rtx_tile_layout", "rtx_deinterleave_async", "rtx_bind_output",
+    "rtx_probe_bandwidth",
 )
 
 
@@ -118,6 +119,10 @@ def load_library():
     lib.rtx_download_u8.argtypes = [vp, vp]
     lib.rtx_device_image.restype = C.c_int
     lib.rtx_device_image.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.rtx_bind_output.restype = C.c_int
+    lib.rtx_bind_output.argtypes = [vp, vp, C.c_size_t]
+    lib.rtx_probe_bandwidth.restype = C.c_int
+    lib.rtx_probe_bandwidth.argtypes = [vp, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     lib.rtx_trace_rays.restype = C.c_int
     lib.rtx_trace_rays.argtypes = [vp, fp, fp, C.c_size_t, C.c_float, u32p, fp]
     lib.rtx_trace_rays_device.restype = C.c_int
@@ -289,6 +294,14 @@ class CudaHost:
         p, n = C.c_void_p(), C.c_size_t()
         self._ck(self._lib.rtx_device_image(self._ctx, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def probe_bandwidth(self, level: int, nbytes: int, iters: int) -> float:
+        g = C.c_double()
+        self._ck(self._lib.rtx_probe_bandwidth(self._ctx, level, nbytes, iters, C.byref(g)))
+        return g.value
+
+    def bind_output(self, device_ptr: int, count: int):
+        self._ck(self._lib.rtx_bind_output(self._ctx, C.c_void_p(device_ptr), count))
 
     def trace_rays(self, origins, dirs, max_distance: float = 100000.0):
         origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 4)

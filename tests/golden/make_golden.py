@@ -1,0 +1,106 @@
+"""Generate the committed golden vectors from the REFERENCE ITSELF.
+
+Run in the build container (needs /root/reference, i.e. oracle/_ref/):
+
+    python tests/golden/make_golden.py
+
+Everything is produced by oracle/_ref/libref_oracle.so -- the reference's own
+kernel text (src/intersect_kernel.cl) and host code (mesh.cc, bvh.cc,
+ray_tracer.cc, compiler_options.h) compiled for the CPU -- never by the
+restatement or the CUDA path.  Outputs (small, committed):
+
+  soup_64x48.npz      float image, hit ids, distances, u8 image of a 300-triangle soup
+  soup_rays.npz       4096 arbitrary rays (incl. axis-parallel ones) and their hits
+  quad_33x17.npz      two big triangles sharing a diagonal, odd image size
+  scenes.json         sha256 digests of the reference builder's arrays + bunny known answers
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from opencl_raytracer_b200 import scenes  # noqa: E402  (mesh generators only)
+from opencl_raytracer_b200.scene import Scene  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def ref_scene(v, f):
+    r = po.ref_scene_from_mesh(v, f)
+    return Scene(r.faces, r.nodes, r.aabbs, r.vertices, r.normals, r.triangles, r.orig_faces)
+
+
+def render_case(sc, w, h, ss, focal=1.0, shading=True):
+    tw, th = po.ref_total_dims(w, h, ss)
+    img = po.ref_render(sc, tw, th, po.ref_focal_roundtrip(focal), shading)
+    fid, dist = po.ref_primary_hits(sc, tw, th, po.ref_focal_roundtrip(focal))
+    u8 = po.ref_resize(img, w, h, ss)
+    return dict(image=img, face_id=fid, distance=dist, u8=u8, width=w, height=h, nss=ss, focal=np.float32(focal),
+                shading=int(shading))
+
+
+def main():
+    assert po.ref() is not None, "oracle/_ref/libref_oracle.so missing: run make -C oracle"
+    digests = {}
+
+    v, f = scenes.random_soup(300, seed=11)
+    sc = ref_scene(v, f)
+    digests["soup300_seed11"] = sc.digest()
+    np.savez_compressed(os.path.join(OUT, "soup_64x48.npz"), verts=v, faces=f, **render_case(sc, 32, 24, 4, focal=1.2345678))
+
+    # arbitrary rays: random + axis-parallel (zero direction components -> 0*inf NaN slabs)
+    lo, hi = sc.root_box()
+    o, d = po.gen_random_rays(1234, 0, 4096 - 64, lo, hi)
+    rng = np.random.default_rng(5)
+    ao = np.zeros((64, 4), np.float32)
+    ad = np.zeros((64, 4), np.float32)
+    ao[:, :3] = rng.uniform(lo, hi, (64, 3))
+    ax = rng.integers(0, 3, 64)
+    ad[np.arange(64), ax] = rng.choice([-1.0, 1.0], 64)
+    ad[np.arange(32, 64), (ax[32:] + 1) % 3] = rng.uniform(-1, 1, 32)           # one zero component only
+    ao[:8, :3] = sc.vertices[sc.faces[:8], :3]                      # origins exactly on vertices / box planes
+    o = np.concatenate([o, ao]); d = np.concatenate([d, ad])
+    fid, dist = po.ref_trace_rays(sc, o, d, 100000.0)
+    fid2, dist2 = po.ref_trace_rays(sc, o, d, 0.75)
+    np.savez_compressed(os.path.join(OUT, "soup_rays.npz"), verts=v, faces=f, origins=o, dirs=d, face_id=fid, distance=dist,
+                        face_id_d075=fid2, distance_d075=dist2)
+
+    v, f = scenes.quad_wall()
+    sc = ref_scene(v, f)
+    digests["quad_wall"] = sc.digest()
+    np.savez_compressed(os.path.join(OUT, "quad_33x17.npz"), verts=v, faces=f, **render_case(sc, 33, 17, 1, shading=False))
+
+    v, f = scenes.sibenik_standin()
+    sc = ref_scene(v, f)
+    digests["sibenik_standin"] = sc.digest()
+    digests["sibenik_standin_tris"] = int(sc.num_triangles)
+
+    kat = {}
+    bunny = "/root/reference/meshes/bunny.off"
+    if os.path.exists(bunny):
+        r = po.ref_scene_from_off(bunny)
+        sc = Scene(r.faces, r.nodes, r.aabbs, r.vertices, r.normals)
+        digests["bunny"] = sc.digest()
+        img = po.ref_render(sc, 1200, 1200, 1.0, True)
+        fid, dist = po.ref_primary_hits(sc, 1200, 1200, 1.0)
+        u8 = po.ref_resize(img, 600, 600, 4)
+        import hashlib
+        kat = dict(nodes=int(sc.nodes.size), nodes_head=[int(x) for x in sc.nodes[:8]], hit_rays=int((fid != po.NO_HIT).sum()),
+                   pgm_mean=float(u8.mean()), pgm_nonzero=int((u8 != 0).sum()),
+                   image_sha256=hashlib.sha256(img.tobytes()).hexdigest(),
+                   face_id_sha256=hashlib.sha256(fid.tobytes()).hexdigest(),
+                   distance_sha256=hashlib.sha256(dist.tobytes()).hexdigest(),
+                   u8_sha256=hashlib.sha256(u8.tobytes()).hexdigest())
+    with open(os.path.join(OUT, "scenes.json"), "w") as fh:
+        json.dump(dict(digests=digests, bunny_c1=kat,
+                       focal_roundtrip={str(x): po.ref_focal_roundtrip(x) for x in (1.0, 1.2345678, 0.5, 3.3333333, 0.001, 123456.789)}),
+                  fh, indent=1, sort_keys=True)
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
