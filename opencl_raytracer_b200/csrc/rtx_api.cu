@@ -59,7 +59,7 @@ struct rtx_ctx {
 	std::string error;
 	/* tunables */
 	int kernel = RTX_KERNEL_PERSISTENT;
-	int leaf_size = 4;
+	int leaf_size = 1;
 	int record_hits = 0;
 	int counters = 0;
 	int top_smem = 0;

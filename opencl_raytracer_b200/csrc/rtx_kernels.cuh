@@ -103,24 +103,43 @@ RTX_DEV void walk_reference(const SceneDev &sc, f3 o, f3 d, float max_distance, 
  * ------------------------------------------------------------------------ */
 struct Slab { float tmin, tmax; };
 
-RTX_DEV Slab slab_minmax(float lx, float ly, float lz, float hx, float hy, float hz, f3 o, f3 id)
+/* Slab interval of one box.  Same products as the literal test ((bb - o) * (1/d), one rounding each);
+ * which of the two products per axis is the entry is decided
+ *   OCT < 4 : at compile time -- bit0 = d.x < 0, bit1 = d.y < 0, d.z < 0 (all lanes of the warp agree);
+ *   OCT = 4 : by min/max, which picks the same product as `div >= 0` whenever no 0*inf occurs.
+ * PRIMARY: the origin is the reference's fixed camera (0,0,2) (intersect_kernel.cl:284): bb.x - 0 and
+ * bb.y - 0 are exact identities and are skipped. */
+template <bool PRIMARY, int OCT>
+RTX_DEV Slab slab_interval(float lx, float ly, float lz, float hx, float hy, float hz, f3 o, f3 id)
 {
-	const float ax = rn_mul(rn_sub(lx, o.x), id.x), bx = rn_mul(rn_sub(hx, o.x), id.x);
-	const float ay = rn_mul(rn_sub(ly, o.y), id.y), by = rn_mul(rn_sub(hy, o.y), id.y);
-	const float az = rn_mul(rn_sub(lz, o.z), id.z), bz = rn_mul(rn_sub(hz, o.z), id.z);
+	const float ax = PRIMARY ? rn_mul(lx, id.x) : rn_mul(rn_sub(lx, o.x), id.x);
+	const float bx = PRIMARY ? rn_mul(hx, id.x) : rn_mul(rn_sub(hx, o.x), id.x);
+	const float ay = PRIMARY ? rn_mul(ly, id.y) : rn_mul(rn_sub(ly, o.y), id.y);
+	const float by = PRIMARY ? rn_mul(hy, id.y) : rn_mul(rn_sub(hy, o.y), id.y);
+	const float az = rn_mul(rn_sub(lz, PRIMARY ? 2.0f : o.z), id.z), bz = rn_mul(rn_sub(hz, PRIMARY ? 2.0f : o.z), id.z);
 	Slab s;
-	s.tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-	s.tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+	if (OCT < 4) {
+		const float nx = (OCT & 1) ? bx : ax, fx = (OCT & 1) ? ax : bx;
+		const float ny = (OCT & 2) ? by : ay, fy = (OCT & 2) ? ay : by;
+		s.tmin = fmaxf(fmaxf(nx, ny), bz);
+		s.tmax = fminf(fminf(fx, fy), az);
+	} else if (PRIMARY) {
+		s.tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), bz);
+		s.tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), az);
+	} else {
+		s.tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+		s.tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+	}
 	return s;
 }
 
-template <int SMEM_STACK, bool TOP_SMEM, bool COUNT>
+template <int SMEM_STACK, bool TOP_SMEM, bool COUNT, bool PRIMARY, int OCT>
 RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ s_top, uint2 *__restrict__ s_stack,
                               f3 o, f3 d, float max_distance, HitRec &best, Counters *cnt)
 {
 	const f3 id = make_f3(rn_div(1.0f, d.x), rn_div(1.0f, d.y), rn_div(1.0f, d.z));
 	/* culling margins in ray-parameter units */
-	const float inv_len = rsqrtf(fmaxf(d.x * d.x + d.y * d.y + d.z * d.z, 1e-30f));
+	const float inv_len = PRIMARY ? 1.0f : rsqrtf(fmaxf(d.x * d.x + d.y * d.y + d.z * d.z, 1e-30f));
 	const float scale = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), sc.scene_scale));
 	const float abs_margin = 1e-5f * scale * inv_len;
 	/* `cull`: ray parameter beyond which nothing can beat the best hit so far.  Boxes also obey the
@@ -128,7 +147,6 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ s_t
 	 * hit at any distance once its leaf box passed. */
 	float cull = __int_as_float(0x7f800000);
 	float limit = max_distance;          /* = min(max_distance, cull), for boxes */
-	float best_r = __int_as_float(0x7f800000);
 	uint2 l_stack[RTX_STACK_MAX - SMEM_STACK];
 	int sp = 0;
 	int cur = 0;                         /* root pair */
@@ -147,26 +165,19 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ s_t
 				q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2); q3 = __ldg(q + 3);
 			}
 			if (COUNT) visits += 2;
-			const Slab L = slab_minmax(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, id);
-			const Slab R = slab_minmax(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, o, id);
+			const Slab L = slab_interval<PRIMARY, OCT>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, id);
+			const Slab R = slab_interval<PRIMARY, OCT>(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, o, id);
 			const bool hitL = L.tmin <= L.tmax && L.tmin < limit && L.tmax > 0.0f;
 			const bool hitR = R.tmin <= R.tmax && R.tmin < limit && R.tmax > 0.0f;
+			if (!(hitL || hitR)) goto pop;
 			const int refL = __float_as_int(q1.z), refR = __float_as_int(q3.z);
+			const bool r_first = hitR && (!hitL || R.tmin < L.tmin);
 			if (hitL && hitR) {
-				const bool r_first = R.tmin < L.tmin;
-				const int near = r_first ? refR : refL, far = r_first ? refL : refR;
-				const float far_t = r_first ? L.tmin : R.tmin;
-				const uint2 e = make_uint2((uint32_t)far, __float_as_uint(far_t));
-				if (sp < SMEM_STACK) s_stack[sp * stride] = e; else l_stack[sp - SMEM_STACK] = e;
+				const uint2 e = make_uint2((uint32_t)(r_first ? refL : refR), __float_as_uint(r_first ? L.tmin : R.tmin));
+				if (SMEM_STACK > 0 && sp < SMEM_STACK) s_stack[sp * stride] = e; else l_stack[sp - SMEM_STACK] = e;
 				++sp;
-				cur = near;
-			} else if (hitL) {
-				cur = refL;
-			} else if (hitR) {
-				cur = refR;
-			} else {
-				goto pop;
 			}
+			cur = r_first ? refR : refL;
 		}
 		/* ---- leaf ---- */
 		{
@@ -185,9 +196,9 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ s_t
 					if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), o, d, max_distance)) continue;
 				}
 				best.dist = h.dist; best.tri = tri; best.s = h.s; best.t = h.t;
-				/* parameter of this hit, recovered from the distance (|P-o| = r|d| up to rounding) */
-				best_r = fminf(best_r, h.dist * inv_len);
-				cull = best_r * 1.0001f + abs_margin;
+				/* hits are accepted in decreasing distance, so this is the smallest so far; its ray
+				 * parameter is recovered from the distance (|P-o| = r|d| up to rounding) */
+				cull = (h.dist * inv_len) * 1.0001f + abs_margin;
 				limit = fminf(max_distance, cull);
 			}
 		}
@@ -195,7 +206,7 @@ pop:
 		for (;;) {
 			if (sp == 0) goto done;
 			--sp;
-			const uint2 e = sp < SMEM_STACK ? s_stack[sp * stride] : l_stack[sp - SMEM_STACK];
+			const uint2 e = (SMEM_STACK > 0 && sp < SMEM_STACK) ? s_stack[sp * stride] : l_stack[sp - SMEM_STACK];
 			if (__uint_as_float(e.y) < limit) { cur = (int)e.x; break; }
 		}
 	}
@@ -207,10 +218,11 @@ done:
 	}
 }
 
-/* One ray through the right path.  Rays with a zero direction component make
- * the reference's slab test produce 0*inf = NaN, whose "never rejects"
- * behaviour only the literal walk reproduces. */
-template <int SMEM_STACK, bool TOP_SMEM, bool COUNT>
+/* One ray through the right path.  Rays with a zero direction component make the reference's slab
+ * test produce 0*inf = NaN, whose propagation only the literal walk reproduces.  For primary rays
+ * (fixed camera, d.z < 0) a warp whose lanes all share the signs of d.x and d.y runs a traversal
+ * specialised for that octant; mixed warps (the image's centre row/column) use the min/max form. */
+template <int SMEM_STACK, bool TOP_SMEM, bool COUNT, bool PRIMARY>
 RTX_DEV void closest_hit(const SceneDev &sc, const float4 *s_top, uint2 *s_stack, bool ordered_ok,
                          f3 o, f3 d, float max_distance, HitRec &best, Counters *cnt)
 {
@@ -219,7 +231,24 @@ RTX_DEV void closest_hit(const SceneDev &sc, const float4 *s_top, uint2 *s_stack
 	best.s = best.t = 0.f;
 	const bool plain = d.x != 0.0f && d.y != 0.0f && d.z != 0.0f;   /* false for NaN too */
 	if (ordered_ok && plain) {
-		traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT>(sc, s_top, s_stack, o, d, max_distance, best, cnt);
+		if (PRIMARY) {
+			const unsigned mask = __activemask();
+			const int oct = (d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0);
+			const int oct0 = __shfl_sync(mask, oct, __ffs(mask) - 1);
+			const bool uniform = __all_sync(mask, oct == oct0) && d.z < 0.0f;
+			if (uniform) {
+				switch (oct0) {
+				case 0: traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, true, 0>(sc, s_top, s_stack, o, d, max_distance, best, cnt); break;
+				case 1: traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, true, 1>(sc, s_top, s_stack, o, d, max_distance, best, cnt); break;
+				case 2: traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, true, 2>(sc, s_top, s_stack, o, d, max_distance, best, cnt); break;
+				default: traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, true, 3>(sc, s_top, s_stack, o, d, max_distance, best, cnt); break;
+				}
+			} else {
+				traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, false, 4>(sc, s_top, s_stack, o, d, max_distance, best, cnt);
+			}
+		} else {
+			traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, false, 4>(sc, s_top, s_stack, o, d, max_distance, best, cnt);
+		}
 	} else {
 		if (COUNT) atomicAdd(&cnt->exact_rays, 1ull);
 		walk_reference<COUNT>(sc, o, d, max_distance, best, cnt);
@@ -263,7 +292,7 @@ RTX_DEV void trace_pixel(const SceneDev &sc, const Work &w, const float4 *s_top,
 	const f3 o = make_f3(0.0f, 0.0f, 2.0f);                           /* :284 */
 	const f3 d = primary_dir(w.cam, x, y);
 	HitRec best;
-	closest_hit<SMEM_STACK, TOP_SMEM, COUNT>(sc, s_top, s_stack, w.ordered_ok != 0, o, d, 100000.0f, best, cnt); /* :292-295 */
+	closest_hit<SMEM_STACK, TOP_SMEM, COUNT, true>(sc, s_top, s_stack, w.ordered_ok != 0, o, d, 100000.0f, best, cnt); /* :292-295 */
 	float value = 0.0f;                                               /* :297-299 */
 	if (best.tri != 0xffffffffu) value = shade_hit(sc.tnormals, best.tri, best.s, best.t, d, w.cam.shading);
 	w.image[out] = value;                                             /* :309 */
@@ -374,7 +403,7 @@ k_trace_rays(const SceneDev sc, const RayWork w, Counters *cnt)
 				random_ray(w.seed, w.first + i, w.bbmin, w.bbmax, o, d);
 			}
 			HitRec best;
-			closest_hit<SMEM_STACK, TOP_SMEM, COUNT>(sc, s_top, s_stack, w.ordered_ok != 0 && !w.exhaustive, o, d, w.max_distance, best, cnt);
+			closest_hit<SMEM_STACK, TOP_SMEM, COUNT, false>(sc, s_top, s_stack, w.ordered_ok != 0 && !w.exhaustive, o, d, w.max_distance, best, cnt);
 			const uint32_t fid = best.tri != 0xffffffffu ? best.tri * 3u : 0xffffffffu;
 			if (w.face_id) w.face_id[i] = fid;
 			if (w.dist) w.dist[i] = best.dist;
