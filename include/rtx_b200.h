@@ -106,6 +106,7 @@ typedef struct rtx_stats {
 #define RTX_TUNE_TOP_SMEM      5  /* node pairs of the top levels staged in shared memory, 0 = off */
 #define RTX_TUNE_BLOCKS_PER_SM 6
 #define RTX_TUNE_FLATTEN_ON_DEVICE 7 /* 1: build the GPU layout with kernels, 0: on the host */
+#define RTX_TUNE_RAYS_PER_THREAD 8 /* primary rays per lane: 1, 2 (2x1 pixels) or 4 (2x2 pixels) */
 
 #define RTX_KERNEL_PERSISTENT  0  /* persistent warps, ordered stack traversal, distance culling */
 #define RTX_KERNEL_EXHAUSTIVE  1  /* one thread per ray, the reference's stackless pre-order walk */

@@ -65,6 +65,7 @@ struct rtx_ctx {
 	int top_smem = 0;
 	int blocks_per_sm = 0;       /* 0 = default of the variant */
 	int flatten_on_device = 0;
+	int rays_per_thread = 4;     /* 1, 2 (2x1) or 4 (2x2) pixels per lane */
 	/* scene */
 	bool uploaded = false;
 	SceneDev sc{};
@@ -238,6 +239,29 @@ cudaError_t launch_render_t(rtx_ctx *c, const Work &w, cudaStream_t st, int bloc
 	return cudaGetLastError();
 }
 
+template <int BLOCK, int MINB, int SST, bool COUNT, bool RECORD, int RX, int RY>
+cudaError_t launch_packet_t(rtx_ctx *c, const Work &w, cudaStream_t st)
+{
+	auto k = k_render_packet<BLOCK, MINB, SST, COUNT, RECORD, RX, RY>;
+	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2);
+	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	int occ = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BLOCK, smem);
+	if (e != cudaSuccess) return e;
+	if (occ < 1) occ = 1;
+	if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
+	k<<<(unsigned)(c->sm_count * occ), BLOCK, smem, st>>>(c->sc, w, c->d_counters.as<Counters>());
+	return cudaGetLastError();
+}
+
+template <bool COUNT, bool RECORD>
+cudaError_t launch_packet(rtx_ctx *c, const Work &w, cudaStream_t st)
+{
+	if (c->rays_per_thread == 2) return launch_packet_t<256, 3, 8, COUNT, RECORD, 2, 1>(c, w, st);
+	return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2>(c, w, st);
+}
+
 template <bool TOP, bool COUNT, bool RECORD>
 cudaError_t launch_render_v(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
@@ -255,6 +279,10 @@ cudaError_t launch_render(rtx_ctx *c, const Work &w, cudaStream_t st)
 		else     { if (rec) k_render_exhaustive<false, true><<<grid, 256, 0, st>>>(c->sc, w, c->d_counters.as<Counters>());
 		           else k_render_exhaustive<false, false><<<grid, 256, 0, st>>>(c->sc, w, c->d_counters.as<Counters>()); }
 		return cudaGetLastError();
+	}
+	if (c->rays_per_thread > 1 && !top) {
+		if (cnt) return rec ? launch_packet<true, true>(c, w, st) : launch_packet<true, false>(c, w, st);
+		return rec ? launch_packet<false, true>(c, w, st) : launch_packet<false, false>(c, w, st);
 	}
 #define RTX_DISPATCH(T, C, R) if (top == T && cnt == C && rec == R) return launch_render_v<T, C, R>(c, w, st)
 	RTX_DISPATCH(false, false, false); RTX_DISPATCH(false, false, true);
@@ -460,6 +488,9 @@ int rtx_set_tunable(rtx_ctx *c, int which, int64_t v)
 		c->top_smem = (int)v; break;
 	case RTX_TUNE_BLOCKS_PER_SM: c->blocks_per_sm = (int)v; break;
 	case RTX_TUNE_FLATTEN_ON_DEVICE: c->flatten_on_device = v != 0; break;
+	case RTX_TUNE_RAYS_PER_THREAD:
+		if (v != 1 && v != 2 && v != 4) return fail(c, RTX_ERR_ARG, "rays per thread must be 1, 2 or 4");
+		c->rays_per_thread = (int)v; break;
 	default: return fail(c, RTX_ERR_ARG, "unknown tunable");
 	}
 	return RTX_OK;
@@ -485,6 +516,20 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 
 	Flat flat;
 	flatten(nodes, aabbs16, nnodes, c->leaf_size, c->top_smem > 0 ? (uint32_t)c->top_smem : 0u, flat);
+	/* Octant copies: copy v swaps lo/hi of x (bit 0) and of y (bit 1) in every node, so that a warp whose
+	 * rays all have d.x < 0 (d.y < 0) finds the entry plane in the "lo" slot without a per-box select. */
+	const size_t pair_vecs = flat.pairs.size();
+	flat.pairs.resize(4 * pair_vecs);
+	for (int v = 1; v < 4; ++v) {
+		float4 *dst = flat.pairs.data() + (size_t)v * pair_vecs;
+		for (size_t i = 0; i < pair_vecs; i += 2) {
+			float4 a = flat.pairs[i], b = flat.pairs[i + 1];     /* a = (lo.x lo.y lo.z hi.x), b = (hi.y hi.z ref 0) */
+			if (v & 1) { const float t = a.x; a.x = a.w; a.w = t; }
+			if (v & 2) { const float t = a.y; a.y = b.x; b.x = t; }
+			dst[i] = a;
+			dst[i + 1] = b;
+		}
+	}
 
 	DevBuf d_faces, d_verts, d_vnormals, d_leaf_node;
 	auto cleanup = [&] { d_faces.release(); d_verts.release(); d_vnormals.release(); d_leaf_node.release(); };
@@ -521,7 +566,7 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	c->sc.tnormals = c->d_tnormals.as<float4>();
 	c->sc.ref_nodes = c->d_ref_nodes.as<uint32_t>();
 	c->sc.ref_aabbs = c->d_ref_aabbs.as<float4>();
-	c->sc.num_pairs = (uint32_t)(flat.pairs.size() / 4);
+	c->sc.num_pairs = (uint32_t)(pair_vecs / 4);
 	c->sc.top_pairs = c->top_smem > 0 ? flat.top_pairs : 0;
 	c->sc.num_tris = (uint32_t)ntris;
 	c->sc.verify_leafbox = c->leaf_size > 1 ? 1u : 0u;

@@ -23,7 +23,7 @@
 #include "rtx_device.cuh"
 
 struct SceneDev {
-	const float4 *pairs;
+	const float4 *pairs;      /* 4 octant copies, each num_pairs * 4 float4 (copy 0 = unswapped) */
 	const float4 *tris;
 	const float4 *leafbox;
 	const float4 *tnormals;
@@ -55,7 +55,7 @@ struct HitRec {
  * triangle in leaf order wins ties.
  * ------------------------------------------------------------------------ */
 template <bool COUNT>
-RTX_DEV void walk_reference(const SceneDev &sc, f3 o, f3 d, float max_distance, HitRec &best, Counters *cnt)
+__device__ __noinline__ void walk_reference(const SceneDev &sc, f3 o, f3 d, float max_distance, HitRec &best, Counters *cnt)
 {
 	const uint32_t n = __ldg(sc.ref_nodes);
 	uint32_t tri = 0;
@@ -105,8 +105,10 @@ struct Slab { float tmin, tmax; };
 
 /* Slab interval of one box.  Same products as the literal test ((bb - o) * (1/d), one rounding each);
  * which of the two products per axis is the entry is decided
- *   OCT < 4 : at compile time -- bit0 = d.x < 0, bit1 = d.y < 0, d.z < 0 (all lanes of the warp agree);
- *   OCT = 4 : by min/max, which picks the same product as `div >= 0` whenever no 0*inf occurs.
+ *   OCT = 0 : by the data -- the warp reads the copy of the pair array whose x/y slots were swapped at
+ *             upload for its octant, so slot "lo" is the entry plane and "hi" the exit plane; d.z < 0;
+ *   OCT = 4 : by min/max, which picks the same product as `div >= 0` whenever no 0*inf occurs
+ *             (symmetric in lo/hi, so it works on any copy).
  * PRIMARY: the origin is the reference's fixed camera (0,0,2) (intersect_kernel.cl:284): bb.x - 0 and
  * bb.y - 0 are exact identities and are skipped. */
 template <bool PRIMARY, int OCT>
@@ -119,10 +121,8 @@ RTX_DEV Slab slab_interval(float lx, float ly, float lz, float hx, float hy, flo
 	const float az = rn_mul(rn_sub(lz, PRIMARY ? 2.0f : o.z), id.z), bz = rn_mul(rn_sub(hz, PRIMARY ? 2.0f : o.z), id.z);
 	Slab s;
 	if (OCT < 4) {
-		const float nx = (OCT & 1) ? bx : ax, fx = (OCT & 1) ? ax : bx;
-		const float ny = (OCT & 2) ? by : ay, fy = (OCT & 2) ? ay : by;
-		s.tmin = fmaxf(fmaxf(nx, ny), bz);
-		s.tmax = fminf(fminf(fx, fy), az);
+		s.tmin = fmaxf(fmaxf(ax, ay), bz);
+		s.tmax = fminf(fminf(bx, by), az);
 	} else if (PRIMARY) {
 		s.tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), bz);
 		s.tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), az);
@@ -134,8 +134,8 @@ RTX_DEV Slab slab_interval(float lx, float ly, float lz, float hx, float hy, flo
 }
 
 template <int SMEM_STACK, bool TOP_SMEM, bool COUNT, bool PRIMARY, int OCT>
-RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ s_top, uint2 *__restrict__ s_stack,
-                              f3 o, f3 d, float max_distance, HitRec &best, Counters *cnt)
+RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ pairs, const float4 *__restrict__ s_top,
+                              uint2 *__restrict__ s_stack, f3 o, f3 d, float max_distance, HitRec &best, Counters *cnt)
 {
 	const f3 id = make_f3(rn_div(1.0f, d.x), rn_div(1.0f, d.y), rn_div(1.0f, d.z));
 	/* culling margins in ray-parameter units */
@@ -157,11 +157,11 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ s_t
 		/* ---- interior: test both children of pair `cur` ---- */
 		while (cur >= 0) {
 			float4 q0, q1, q2, q3;
-			if (TOP_SMEM && (uint32_t)cur < sc.top_pairs) {
+			if (TOP_SMEM && OCT == 4 && (uint32_t)cur < sc.top_pairs) {
 				const float4 *q = s_top + 4 * cur;
 				q0 = q[0]; q1 = q[1]; q2 = q[2]; q3 = q[3];
 			} else {
-				const float4 *q = sc.pairs + 4 * (size_t)cur;
+				const float4 *q = pairs + 4 * (size_t)cur;
 				q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2); q3 = __ldg(q + 3);
 			}
 			if (COUNT) visits += 2;
@@ -236,18 +236,12 @@ RTX_DEV void closest_hit(const SceneDev &sc, const float4 *s_top, uint2 *s_stack
 			const int oct = (d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0);
 			const int oct0 = __shfl_sync(mask, oct, __ffs(mask) - 1);
 			const bool uniform = __all_sync(mask, oct == oct0) && d.z < 0.0f;
-			if (uniform) {
-				switch (oct0) {
-				case 0: traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, true, 0>(sc, s_top, s_stack, o, d, max_distance, best, cnt); break;
-				case 1: traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, true, 1>(sc, s_top, s_stack, o, d, max_distance, best, cnt); break;
-				case 2: traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, true, 2>(sc, s_top, s_stack, o, d, max_distance, best, cnt); break;
-				default: traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, true, 3>(sc, s_top, s_stack, o, d, max_distance, best, cnt); break;
-				}
-			} else {
-				traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, false, 4>(sc, s_top, s_stack, o, d, max_distance, best, cnt);
-			}
+			if (uniform)
+				traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, true, 0>(sc, sc.pairs + (size_t)oct0 * sc.num_pairs * 4, s_top, s_stack, o, d, max_distance, best, cnt);
+			else
+				traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, false, 4>(sc, sc.pairs, s_top, s_stack, o, d, max_distance, best, cnt);
 		} else {
-			traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, false, 4>(sc, s_top, s_stack, o, d, max_distance, best, cnt);
+			traverse_ordered<SMEM_STACK, TOP_SMEM, COUNT, false, 4>(sc, sc.pairs, s_top, s_stack, o, d, max_distance, best, cnt);
 		}
 	} else {
 		if (COUNT) atomicAdd(&cnt->exact_rays, 1ull);
@@ -326,6 +320,199 @@ k_render_persistent(const SceneDev sc, const Work w, Counters *cnt)
 		size_t out;
 		if (unit_pixel(w, unit, lane, x, y, out))
 			trace_pixel<SMEM_STACK, TOP_SMEM, COUNT, RECORD>(sc, w, s_top, s_stack, x, y, out, cnt);
+		__syncwarp();
+	}
+}
+
+/* --------------------------------------------------------------------------
+ * Thread-level ray packets.  ncu on the one-ray-per-thread kernel (profiles/)
+ * shows the LSU register write-back saturated (~90 %): every lane pulls the
+ * same 64-byte node pair through L1 for one ray's 26 flops.  Here each lane
+ * carries NR = RX x RY neighbouring pixels and walks the tree ONCE for them:
+ * a pair is loaded once per lane and slab-tested against all NR rays, a child
+ * is entered if any ray enters it, a triangle is loaded once and tested by the
+ * rays whose own test of its leaf box passed.  Per ray nothing changes: child
+ * boxes lie inside parent boxes and the slab test is monotone, so a ray that
+ * failed a box fails everything below it -- its own candidate set, order of
+ * acceptance (min distance, ties to the smaller leaf index) and culling bound
+ * are exactly those of the single-ray traversal.
+ * ------------------------------------------------------------------------ */
+template <int NR, int SMEM_STACK, bool COUNT, int OCT>
+RTX_DEV void traverse_packet(const SceneDev &sc, const float4 *__restrict__ pairs, uint2 *__restrict__ s_stack,
+                             const f3 (&d)[NR], uint32_t active, HitRec (&best)[NR], Counters *cnt)
+{
+	const float max_distance = 100000.0f;                              /* intersect_kernel.cl:292 */
+	const f3 o = make_f3(0.0f, 0.0f, 2.0f);                            /* :284 */
+	f3 id[NR];
+	float cull[NR], limit[NR];
+#pragma unroll
+	for (int r = 0; r < NR; ++r) {
+		id[r] = make_f3(rn_div(1.0f, d[r].x), rn_div(1.0f, d[r].y), rn_div(1.0f, d[r].z));
+		cull[r] = __int_as_float(0x7f800000);
+		limit[r] = (active >> r) & 1u ? max_distance : __int_as_float(0xff800000);   /* -inf: enters nothing */
+	}
+	const float abs_margin = 1e-5f * fmaxf(2.0f, sc.scene_scale);     /* |d| = 1 */
+	uint2 l_stack[RTX_STACK_MAX - SMEM_STACK];
+	int sp = 0;
+	int cur = 0;
+	uint32_t mask = 0;                   /* rays that entered the box of `cur` */
+	unsigned long long visits = 0, tests = 0, lbtests = 0;
+	const int stride = blockDim.x;
+	constexpr uint32_t MBITS = (1u << NR) - 1u;
+
+	for (;;) {
+		while (cur >= 0) {
+			const float4 *q = pairs + 4 * (size_t)cur;
+			const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+			if (COUNT) visits += 2 * NR;
+			uint32_t mL = 0, mR = 0;
+			float tL = __int_as_float(0x7f800000), tR = __int_as_float(0x7f800000);
+#pragma unroll
+			for (int r = 0; r < NR; ++r) {
+				const Slab L = slab_interval<true, OCT>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, id[r]);
+				const Slab R = slab_interval<true, OCT>(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, o, id[r]);
+				const bool hl = L.tmin <= L.tmax && L.tmin < limit[r] && L.tmax > 0.0f;
+				const bool hr = R.tmin <= R.tmax && R.tmin < limit[r] && R.tmax > 0.0f;
+				if (hl) { mL |= 1u << r; tL = fminf(tL, L.tmin); }
+				if (hr) { mR |= 1u << r; tR = fminf(tR, R.tmin); }
+			}
+			if (!(mL | mR)) goto pop;
+			const int refL = __float_as_int(q1.z), refR = __float_as_int(q3.z);
+			const bool r_first = mR && (!mL || tR < tL);
+			if (mL && mR) {
+				/* entry = (ref, entry parameter with the ray mask in its 4 low mantissa bits) */
+				const uint32_t tbits = (__float_as_uint(r_first ? tL : tR) & ~0xFu) | (r_first ? mL : mR);
+				const uint2 e = make_uint2((uint32_t)(r_first ? refL : refR), tbits);
+				if (SMEM_STACK > 0 && sp < SMEM_STACK) s_stack[sp * stride] = e; else l_stack[sp - SMEM_STACK] = e;
+				++sp;
+			}
+			cur = r_first ? refR : refL;
+			mask = r_first ? mR : mL;
+		}
+		{
+			const uint32_t enc = ~(uint32_t)cur;
+			const uint32_t first = enc >> 3, count = (enc & 7u) + 1u;
+			for (uint32_t k = 0; k < count; ++k) {
+				const uint32_t tri = first + k;
+				const float4 *q = sc.tris + 4 * (size_t)tri;
+				const float4 t0 = __ldg(q), t1 = __ldg(q + 1), t2 = __ldg(q + 2), t3 = __ldg(q + 3);
+#pragma unroll
+				for (int r = 0; r < NR; ++r) {
+					if (!((mask >> r) & 1u)) continue;
+					TriHit h;
+					if (COUNT) ++tests;
+					if (!triangle_test(t0, t1, t2, t3, o, d[r], cull[r], h)) continue;
+					if (!(h.dist < best[r].dist || (h.dist == best[r].dist && tri < best[r].tri))) continue;
+					if (sc.verify_leafbox) {
+						const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+						if (COUNT) ++lbtests;
+						if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), o, d[r], max_distance)) continue;
+					}
+					best[r].dist = h.dist; best[r].tri = tri; best[r].s = h.s; best[r].t = h.t;
+					cull[r] = h.dist * 1.0001f + abs_margin;
+					limit[r] = fminf(max_distance, cull[r]);
+				}
+			}
+		}
+pop:
+		for (;;) {
+			if (sp == 0) goto done;
+			--sp;
+			const uint2 e = (SMEM_STACK > 0 && sp < SMEM_STACK) ? s_stack[sp * stride] : l_stack[sp - SMEM_STACK];
+			const float t = __uint_as_float(e.y & ~0xFu);
+			uint32_t m = 0;
+#pragma unroll
+			for (int r = 0; r < NR; ++r)
+				if (t < limit[r]) m |= 1u << r;
+			m &= e.y & MBITS;
+			if (m) { cur = (int)e.x; mask = m; break; }
+		}
+	}
+done:
+	if (COUNT) {
+		atomicAdd(&cnt->node_visits, visits);
+		atomicAdd(&cnt->tri_tests, tests);
+		atomicAdd(&cnt->leafbox_tests, lbtests);
+	}
+}
+
+/* Persistent packet kernel: a warp's unit of work is an (8 RX) x (4 RY) pixel block, lane (lx, ly) of the
+ * 8 x 4 lane grid owns the RX x RY pixels at (lx RX, ly RY).  32x32 tiles hold 32 / (RX RY) units. */
+template <int BLOCK, int MIN_BLOCKS, int SMEM_STACK, bool COUNT, bool RECORD, int RX, int RY>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
+k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
+{
+	constexpr int NR = RX * RY;
+	constexpr uint32_t UPT = 32u / NR;                 /* units per tile */
+	constexpr uint32_t UX = RTX_TILE / (8 * RX);       /* units per tile row */
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint2 *s_stack = reinterpret_cast<uint2 *>(smem_raw) + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31u;
+	const f3 o = make_f3(0.0f, 0.0f, 2.0f);
+	for (;;) {
+		uint32_t unit = 0;
+		if (lane == 0) unit = atomicAdd(w.counter, 1u);
+		unit = __shfl_sync(0xffffffffu, unit, 0);
+		if (unit >= w.local_tiles * UPT) break;
+		const uint32_t ltile = unit / UPT, sub = unit % UPT;
+		const uint32_t tile = ltile * w.world + w.rank;
+		const uint32_t tx = tile % w.tiles_x, ty = tile / w.tiles_x;
+		const uint32_t px0 = (sub % UX) * (8 * RX) + (lane & 7u) * RX, py0 = (sub / UX) * (4 * RY) + (lane >> 3) * RY;
+		f3 d[NR];
+		HitRec best[NR];
+		size_t out[NR];
+		uint32_t valid = 0, packet = 0;
+		int oct = -1;
+		bool same = true;
+#pragma unroll
+		for (int r = 0; r < NR; ++r) {
+			const uint32_t px = px0 + (r % RX), py = py0 + (r / RX);
+			const uint32_t x = tx * RTX_TILE + px, y = ty * RTX_TILE + py;
+			out[r] = w.world > 1 ? (size_t)ltile * (RTX_TILE * RTX_TILE) + py * RTX_TILE + px : (size_t)y * w.cam.W + x;
+			best[r].dist = __int_as_float(0x7f800000); best[r].tri = 0xffffffffu; best[r].s = best[r].t = 0.f;
+			d[r] = primary_dir(w.cam, x, y);
+			if (ty < w.tiles_y && x < w.cam.W && y < w.cam.H) {
+				valid |= 1u << r;
+				if (d[r].x != 0.0f && d[r].y != 0.0f && d[r].z != 0.0f) {
+					packet |= 1u << r;
+					const int oc = (d[r].x < 0.0f ? 1 : 0) | (d[r].y < 0.0f ? 2 : 0) | (d[r].z < 0.0f ? 0 : 4);
+					if (oct < 0) oct = oc; else same = same && oc == oct;
+				}
+			}
+		}
+		if (!w.ordered_ok) packet = 0;
+		/* all packet rays of the warp in one octant (d.z < 0)?  then the compile-time entry/exit form */
+		const unsigned anyp = __ballot_sync(0xffffffffu, packet != 0);
+		if (anyp) {
+			const int src = __ffs(anyp) - 1;
+			const int oct0 = __shfl_sync(0xffffffffu, oct, src);
+			const bool uniform = __all_sync(0xffffffffu, packet == 0 || (same && oct == oct0)) && oct0 < 4;
+			if (packet) {
+				if (uniform) {
+					traverse_packet<NR, SMEM_STACK, COUNT, 0>(sc, sc.pairs + (size_t)oct0 * sc.num_pairs * 4, s_stack, d, packet, best, cnt);
+				} else {
+#pragma unroll 1
+					for (int r = 0; r < NR; ++r)
+						if ((packet >> r) & 1u)
+							traverse_ordered<SMEM_STACK, false, COUNT, false, 4>(sc, sc.pairs, nullptr, s_stack, o, d[r], 100000.0f, best[r], cnt);
+				}
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < NR; ++r) {
+			if (!((valid >> r) & 1u)) continue;
+			if (!((packet >> r) & 1u)) {                 /* zero direction component or deep tree: literal walk */
+				if (COUNT) atomicAdd(&cnt->exact_rays, 1ull);
+				walk_reference<COUNT>(sc, o, d[r], 100000.0f, best[r], cnt);
+			}
+			float value = 0.0f;
+			if (best[r].tri != 0xffffffffu) value = shade_hit(sc.tnormals, best[r].tri, best[r].s, best[r].t, d[r], w.cam.shading);
+			w.image[out[r]] = value;
+			if (RECORD) {
+				w.face_id[out[r]] = best[r].tri != 0xffffffffu ? best[r].tri * 3u : 0xffffffffu;
+				w.dist[out[r]] = best[r].dist;
+			}
+		}
 		__syncwarp();
 	}
 }

@@ -26,7 +26,7 @@ NO_HIT = 0xFFFFFFFF
 
 OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NOMEM = range(7)
 
-TUNE_KERNEL, TUNE_LEAF_SIZE, TUNE_RECORD_HITS, TUNE_COUNTERS, TUNE_TOP_SMEM, TUNE_BLOCKS_PER_SM, TUNE_FLATTEN_ON_DEVICE = range(1, 8)
+TUNE_KERNEL, TUNE_LEAF_SIZE, TUNE_RECORD_HITS, TUNE_COUNTERS, TUNE_TOP_SMEM, TUNE_BLOCKS_PER_SM, TUNE_FLATTEN_ON_DEVICE, TUNE_RAYS_PER_THREAD = range(1, 9)
 KERNEL_PERSISTENT, KERNEL_EXHAUSTIVE = 0, 1
 
 # every symbol include/rtx_b200.h declares (tests check the library exports them all)
@@ -212,6 +212,10 @@ class CudaHost:
         _check(self._lib, None, self._lib.rtx_create(C.byref(self._ctx), C.byref(self._opt)))
         self.tile_world = max(1, tile_world)
         self.tile_rank = tile_rank if tile_world > 1 else 0
+        # experiment hook: RTX_TUNE="rays_per_thread=2,leaf_size=4" overrides the library defaults
+        for kv in filter(None, os.environ.get("RTX_TUNE", "").split(",")):
+            k, v = kv.split("=")
+            self.set_tunable(globals()["TUNE_" + k.strip().upper()], int(v))
 
     # -- lifetime --
     def close(self):

@@ -40,19 +40,19 @@ def main():
     host.CudaHost.printInfo()
     for name in names:
         sc = get_scene(name)
-        w, h, ss = (600, 600, 4) if name != "sibenik" else (960, 540, 4)
+        w, h, ss = (600, 600, 4) if name != "sibenik" else (1920, 1080, 4)
         rt = host.RayTracer(host.Options(width=w, height=h, nSuperSamples=ss))
         print("== %s: %d tris, %d nodes, %dx%d rays" % (sc.name, sc.num_triangles, sc.num_nodes, rt.totalWidth, rt.totalHeight))
         t = time.time()
         ref = po.render(sc, rt.totalWidth, rt.totalHeight, 1.0, True, want_counters=True)
         print("  oracle: %.2fs  V=%.2f T=%.3f h=%.4f" % (time.time() - t, ref.counters["V"], ref.counters["T"], ref.counters["h"]))
-        for kernel, leaf, top in ((host.KERNEL_EXHAUSTIVE, 1, 0), (host.KERNEL_PERSISTENT, 1, 0), (host.KERNEL_PERSISTENT, 2, 0),
-                                  (host.KERNEL_PERSISTENT, 4, 0), (host.KERNEL_PERSISTENT, 8, 0), (host.KERNEL_PERSISTENT, 4, 127),
-                                  (host.KERNEL_PERSISTENT, 4, 511)):
+        for kernel, leaf, top, rpt in ((host.KERNEL_EXHAUSTIVE, 1, 0, 1), (host.KERNEL_PERSISTENT, 1, 0, 1), (host.KERNEL_PERSISTENT, 1, 0, 2),
+                                       (host.KERNEL_PERSISTENT, 1, 0, 4), (host.KERNEL_PERSISTENT, 2, 0, 4), (host.KERNEL_PERSISTENT, 4, 0, 4)):
             with host.CudaHost(rt) as hst:
                 hst.set_tunable(host.TUNE_KERNEL, kernel)
                 hst.set_tunable(host.TUNE_LEAF_SIZE, leaf)
                 hst.set_tunable(host.TUNE_TOP_SMEM, top)
+                hst.set_tunable(host.TUNE_RAYS_PER_THREAD, rpt)
                 hst.set_tunable(host.TUNE_RECORD_HITS, 1)
                 hst.set_tunable(host.TUNE_COUNTERS, 1)
                 t = time.time(); hst.upload_scene(sc); t_up = time.time() - t
@@ -60,7 +60,7 @@ def main():
                 st = hst.stats()
                 img = hst.download()
                 fid, dist = hst.download_hits()
-                tag = "%s leaf=%d top=%d" % ("exhaustive" if kernel else "persistent", leaf, top)
+                tag = "%s leaf=%d top=%d rpt=%d" % ("exhaustive" if kernel else "persistent", leaf, top, rpt)
                 compare(tag, fid, dist, img, ref)
                 rays = st["rays"]
                 print("    counters: visits/ray %.2f tri/ray %.3f leafbox/ray %.3f exact rays %d depth %d pairs %d upload %.1f ms" % (
