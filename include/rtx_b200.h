@@ -96,6 +96,7 @@ typedef struct rtx_stats {
 	uint64_t exact_path_rays;   /* rays routed to the reference-order walk */
 	uint32_t tree_depth;        /* depth of the flattened tree (stack need) */
 	uint32_t num_pairs;         /* internal nodes of the flattened tree */
+	uint64_t packet_overflows;  /* packets whose frustum lists overflowed (fell back to per-ray traversal) */
 } rtx_stats;
 
 /* Tunables (rtx_set_tunable).  Defaults are the measured best. */
@@ -107,6 +108,7 @@ typedef struct rtx_stats {
 #define RTX_TUNE_BLOCKS_PER_SM 6
 #define RTX_TUNE_FLATTEN_ON_DEVICE 7 /* 1: build the GPU layout with kernels, 0: on the host */
 #define RTX_TUNE_RAYS_PER_THREAD 8 /* primary rays per lane: 1, 2 (2x1 pixels) or 4 (2x2 pixels) */
+#define RTX_TUNE_FRUSTUM       9  /* frustum front end for 16x8-pixel packets: 0 off, 1 on, -1 auto */
 
 #define RTX_KERNEL_PERSISTENT  0  /* persistent warps, ordered stack traversal, distance culling */
 #define RTX_KERNEL_EXHAUSTIVE  1  /* one thread per ray, the reference's stackless pre-order walk */

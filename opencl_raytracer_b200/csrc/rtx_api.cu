@@ -66,6 +66,7 @@ struct rtx_ctx {
 	int blocks_per_sm = 0;       /* 0 = default of the variant */
 	int flatten_on_device = 0;
 	int rays_per_thread = 4;     /* 1, 2 (2x1) or 4 (2x2) pixels per lane */
+	int frustum = -1;            /* frustum front end: 0 off, 1 on, -1 auto (rays per triangle >= 24) */
 	/* scene */
 	bool uploaded = false;
 	SceneDev sc{};
@@ -76,7 +77,7 @@ struct rtx_ctx {
 	uint32_t W = 0, H = 0, tiles_x = 0, tiles_y = 0, tiles_per_rank = 0, local_tiles = 0;
 	uint32_t rank = 0, world = 1;
 	float *ext_image = nullptr;  /* caller-owned output (rtx_bind_output) */
-	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums;
+	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums, d_lists;
 	bool rendered = false, full_valid = false;
 	/* stats */
 	rtx_stats stats{};
@@ -239,11 +240,11 @@ cudaError_t launch_render_t(rtx_ctx *c, const Work &w, cudaStream_t st, int bloc
 	return cudaGetLastError();
 }
 
-template <int BLOCK, int MINB, int SST, bool COUNT, bool RECORD, int RX, int RY>
+template <int BLOCK, int MINB, int SST, bool COUNT, bool RECORD, int RX, int RY, bool FRUSTUM>
 cudaError_t launch_packet_t(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
-	auto k = k_render_packet<BLOCK, MINB, SST, COUNT, RECORD, RX, RY>;
-	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2);
+	auto k = k_render_packet<BLOCK, MINB, SST, COUNT, RECORD, RX, RY, FRUSTUM>;
+	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2) + (FRUSTUM ? (size_t)(BLOCK / 32) * (2 * RTX_CCAP) * 4 : 0);
 	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	int occ = 0;
@@ -258,8 +259,9 @@ cudaError_t launch_packet_t(rtx_ctx *c, const Work &w, cudaStream_t st)
 template <bool COUNT, bool RECORD>
 cudaError_t launch_packet(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
-	if (c->rays_per_thread == 2) return launch_packet_t<256, 3, 8, COUNT, RECORD, 2, 1>(c, w, st);
-	return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2>(c, w, st);
+	if (c->rays_per_thread == 2) return launch_packet_t<256, 3, 8, COUNT, RECORD, 2, 1, false>(c, w, st);
+	if (w.frustum) return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, true>(c, w, st);
+	return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, false>(c, w, st);
 }
 
 template <bool TOP, bool COUNT, bool RECORD>
@@ -331,6 +333,7 @@ int finish_stats(rtx_ctx *c)
 		c->stats.tri_tests = h.tri_tests;
 		c->stats.leafbox_tests = h.leafbox_tests;
 		c->stats.exact_path_rays = h.exact_rays;
+		c->stats.packet_overflows = h.overflow_packets;
 	}
 	return RTX_OK;
 }
@@ -463,7 +466,7 @@ void rtx_destroy(rtx_ctx *c)
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = { &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
-	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums };
+	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists };
 	for (DevBuf *b : bufs) b->release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
@@ -488,6 +491,9 @@ int rtx_set_tunable(rtx_ctx *c, int which, int64_t v)
 		c->top_smem = (int)v; break;
 	case RTX_TUNE_BLOCKS_PER_SM: c->blocks_per_sm = (int)v; break;
 	case RTX_TUNE_FLATTEN_ON_DEVICE: c->flatten_on_device = v != 0; break;
+	case RTX_TUNE_FRUSTUM:
+		if (v < -1 || v > 1) return fail(c, RTX_ERR_ARG, "frustum must be -1, 0 or 1");
+		c->frustum = (int)v; break;
 	case RTX_TUNE_RAYS_PER_THREAD:
 		if (v != 1 && v != 2 && v != 4) return fail(c, RTX_ERR_ARG, "rays per thread must be 1, 2 or 4");
 		c->rays_per_thread = (int)v; break;
@@ -612,15 +618,28 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	w.face_id = c->record_hits ? c->d_face_id.as<uint32_t>() : nullptr;
 	w.dist = c->record_hits ? c->d_dist.as<float>() : nullptr;
 	w.ordered_ok = c->tree_depth <= RTX_STACK_MAX ? 1 : 0;
+	/* frustum front end pays off when packets see few triangles: many rays per triangle */
+	const double rays_per_tri = (double)c->W * c->H / (double)c->sc.num_tris;
+	w.frustum = (c->frustum == 1 || (c->frustum < 0 && rays_per_tri >= 24.0)) && c->rays_per_thread == 4 && w.ordered_ok ? 1 : 0;
+	const bool persistent = !(c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok);
+	if (!persistent || c->top_smem > 0) w.frustum = 0;
+	if (w.frustum) {
+		CU(c, c->d_lists.alloc((size_t)c->local_tiles * RTX_LIST_STRIDE * 4));
+		w.lists = c->d_lists.as<uint32_t>();
+	}
 	CU(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
 	if (c->counters) CU(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(Counters), st));
 	CU(c, cudaEventRecord(c->ev0, st));
+	if (w.frustum && c->local_tiles > 0) {
+		k_frustum_collect<<<(c->local_tiles + 7) / 8, 256, 0, st>>>(c->sc, w, c->d_lists.as<uint32_t>());
+		CU(c, cudaGetLastError());
+	}
 	CU(c, launch_render(c, w, st));
 	CU(c, cudaEventRecord(c->ev1, st));
 	c->ev_pending = true;
 	c->stats.rays = (uint64_t)c->local_tiles * RTX_TILE * RTX_TILE;
 	if (c->world == 1) c->stats.rays = (uint64_t)c->W * c->H;
-	c->stats.kernel_launches = 1;
+	c->stats.kernel_launches = w.frustum ? 2 : 1;
 	c->stats.kernel_variant = (c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
 	c->rendered = true;
 	c->full_valid = false;

@@ -37,7 +37,7 @@ struct SceneDev {
 };
 
 struct Counters {
-	unsigned long long node_visits, tri_tests, leafbox_tests, exact_rays;
+	unsigned long long node_visits, tri_tests, leafbox_tests, exact_rays, overflow_packets;
 };
 
 struct HitRec {
@@ -265,6 +265,8 @@ struct Work {
 	uint32_t *face_id;           /* optional (record mode), same indexing as image */
 	float *dist;
 	int ordered_ok;
+	int frustum;                 /* use the frustum front end for packets */
+	const uint32_t *lists;       /* per-tile candidate lists written by k_frustum_collect */
 };
 
 RTX_DEV bool unit_pixel(const Work &w, uint32_t unit, uint32_t lane, uint32_t &x, uint32_t &y, size_t &out)
@@ -436,9 +438,210 @@ done:
 	}
 }
 
+/* --------------------------------------------------------------------------
+ * Frustum front end for coherent primary-ray packets.
+ *
+ * A warp's 16x8-pixel packet (128 rays from the fixed camera) is a thin frustum: on the sibenik stand-in
+ * at 4K the union over the packet of all leaf boxes any of its rays enters is ~11 triangles, barely more
+ * than one ray's own ~9 (tools/packet_stats.py).  So the tree is walked ONCE per packet against the
+ * frustum (level 1, lanes in parallel over a breadth-first queue), giving a short depth-sorted list of
+ * candidate leaves, and each ray then runs the reference's own two tests over that list (level 2): the
+ * literal-equivalent slab test of the triangle's leaf box and the triangle test.  Per ray this is exactly
+ * the reference's candidate rule (point 1): interior boxes only steer the search, so a
+ * conservative frustum test may replace 128 per-ray tests.  The frustum test is widened by 1e-4 of the
+ * scene scale, far above float rounding, so no leaf a ray's own slab test would pass is ever dropped.
+ * Queue or list overflow (a packet grazing hundreds of triangles) falls back to the per-ray traversal.
+ * ------------------------------------------------------------------------ */
+#define RTX_QCAP 128     /* breadth-first queue of node pairs, per warp */
+#define RTX_CCAP 192     /* candidate leaves per 32x32-pixel tile */
+#define RTX_LIST_STRIDE (2 * RTX_CCAP + 4)   /* words per tile list: [count, pad x3, enc[CCAP], key[CCAP]] */
+
+struct Frustum { float u0, u1, v0, v1, margin; };   /* ray = (0,0,2) + s * (u, v, -1), s >= 0 */
+
+/* Frustum of the pixel rectangle [X0, X0+PW) x [Y0, Y0+PH) (covers any sub-pixel offset, jittered or not). */
+RTX_DEV Frustum make_frustum(const Camera &cam, float X0, float Y0, float PW, float PH, float scene_scale)
+{
+	Frustum f;
+	const float ua = X0 / cam.a - cam.w_over_2a, ub = (X0 + PW) / cam.a - cam.w_over_2a;
+	const float va = -(Y0 / cam.a - cam.h_over_2a), vb = -((Y0 + PH) / cam.a - cam.h_over_2a);
+	f.margin = 1e-4f * fmaxf(2.0f, scene_scale);
+	f.u0 = fminf(ua, ub) - 1e-5f; f.u1 = fmaxf(ua, ub) + 1e-5f;
+	f.v0 = fminf(va, vb) - 1e-5f; f.v1 = fmaxf(va, vb) + 1e-5f;
+	return f;
+}
+
+/* Does the box reach into the frustum?  s = depth along -z.  Returns the (conservative) entry depth. */
+RTX_DEV bool frustum_box(float lx, float ly, float lz, float hx, float hy, float hz, const Frustum &f, float &entry)
+{
+	const float s1 = (2.0f - lz) + f.margin;                 /* far depth */
+	const float s0 = fmaxf((2.0f - hz) - f.margin, 0.0f);    /* near depth, clamped to the camera plane */
+	entry = s0;
+	const float xa = f.u0 * s0, xb = f.u0 * s1, xc = f.u1 * s0, xd = f.u1 * s1;
+	const float ya = f.v0 * s0, yb = f.v0 * s1, yc = f.v1 * s0, yd = f.v1 * s1;
+	return s1 > 0.0f &&
+	       hx >= fminf(xa, xb) - f.margin && lx <= fmaxf(xc, xd) + f.margin &&
+	       hy >= fminf(ya, yb) - f.margin && ly <= fmaxf(yc, yd) + f.margin;
+}
+
+/* Level 1 kernel: one warp per 32x32-pixel tile walks the tree breadth-first against the tile's frustum,
+ * lanes in parallel over the queue, and writes the tile's candidate leaves sorted by entry depth.
+ * count = -1: queue or list overflow, the tile's packets use the per-ray traversal. */
+__global__ void __launch_bounds__(256)
+k_frustum_collect(const SceneDev sc, const Work w, uint32_t *__restrict__ lists)
+{
+	__shared__ int s_queue_all[8][RTX_QCAP];
+	__shared__ uint32_t s_tmp_all[8][RTX_CCAP];
+	__shared__ float s_tkey_all[8][RTX_CCAP];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t ltile = blockIdx.x * 8 + warp;
+	if (ltile >= w.local_tiles) return;
+	int *s_queue = s_queue_all[warp];
+	uint32_t *s_tmp = s_tmp_all[warp];
+	float *s_tkey = s_tkey_all[warp];
+	const uint32_t tile = ltile * w.world + w.rank;
+	const uint32_t tx = tile % w.tiles_x, ty = tile / w.tiles_x;
+	const Frustum f = make_frustum(w.cam, (float)(tx * RTX_TILE), (float)(ty * RTX_TILE), (float)RTX_TILE, (float)RTX_TILE, sc.scene_scale);
+	uint32_t *out = lists + (size_t)ltile * RTX_LIST_STRIDE;
+	const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+	int head = 0, tail = 1, ncand = 0;
+	if (lane == 0) s_queue[0] = 0;
+	__syncwarp();
+	while (head < tail) {
+		const int n = min(32, tail - head);
+		bool iL = false, iR = false, fL = false, fR = false;
+		int refL = 0, refR = 0;
+		float eL = 0.f, eR = 0.f;
+		if ((int)lane < n) {
+			const int pair = s_queue[(head + lane) % RTX_QCAP];
+			const float4 *q = sc.pairs + 4 * (size_t)pair;
+			const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+			const bool pL = frustum_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, f, eL);
+			const bool pR = frustum_box(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, f, eR);
+			refL = __float_as_int(q1.z); refR = __float_as_int(q3.z);
+			iL = pL && refL >= 0; fL = pL && refL < 0;
+			iR = pR && refR >= 0; fR = pR && refR < 0;
+		}
+		head += n;
+		const unsigned bIL = __ballot_sync(full, iL), bIR = __ballot_sync(full, iR);
+		const unsigned bFL = __ballot_sync(full, fL), bFR = __ballot_sync(full, fR);
+		const int nI = __popc(bIL) + __popc(bIR), nF = __popc(bFL) + __popc(bFR);
+		if (tail - head + nI > RTX_QCAP || ncand + nF > RTX_CCAP) { ncand = -1; break; }
+		if (iL) s_queue[(tail + __popc(bIL & lt)) % RTX_QCAP] = refL;
+		if (iR) s_queue[(tail + __popc(bIL) + __popc(bIR & lt)) % RTX_QCAP] = refR;
+		if (fL) { const int k = ncand + __popc(bFL & lt); s_tmp[k] = ~(uint32_t)refL; s_tkey[k] = eL; }
+		if (fR) { const int k = ncand + __popc(bFL) + __popc(bFR & lt); s_tmp[k] = ~(uint32_t)refR; s_tkey[k] = eR; }
+		tail += nI;
+		ncand += nF;
+		__syncwarp();
+	}
+	if (lane == 0) out[0] = (uint32_t)ncand;
+	/* rank sort by entry depth (ties by position): the list is short */
+	for (int i = lane; i < ncand; i += 32) {
+		const float ki = s_tkey[i];
+		int rank = 0;
+		for (int j = 0; j < ncand; ++j) {
+			const float kj = s_tkey[j];
+			rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+		}
+		out[4 + rank] = s_tmp[i];
+		out[4 + RTX_CCAP + rank] = __float_as_uint(ki);
+	}
+}
+
+/* A packet's share of its tile's list: lanes test the candidates' leaf boxes against the packet's own
+ * (16x8-pixel) frustum in parallel and compact the survivors, order preserved, into shared memory. */
+RTX_DEV int filter_candidates(const SceneDev &sc, const Frustum &f, const uint32_t *__restrict__ list, int n,
+                              uint32_t *__restrict__ s_cand, float *__restrict__ s_key, uint32_t lane)
+{
+	const unsigned lt = (1u << lane) - 1u;
+	int m = 0;
+	for (int base = 0; base < n; base += 32) {
+		const int i = base + (int)lane;
+		bool keep = false;
+		uint32_t enc = 0;
+		float key = 0.f;
+		if (i < n) {
+			enc = __ldg(list + 4 + i);
+			key = __uint_as_float(__ldg(list + 4 + RTX_CCAP + i));
+			keep = true;
+			if ((enc & 7u) == 0u) {                       /* single-triangle leaf: its box is the triangle's leaf box */
+				const uint32_t tri = enc >> 3;
+				const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+				float e;
+				keep = frustum_box(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, f, e);
+			}
+		}
+		const unsigned b = __ballot_sync(0xffffffffu, keep);
+		if (keep) { const int k = m + __popc(b & lt); s_cand[k] = enc; s_key[k] = key; }
+		m += __popc(b);
+	}
+	__syncwarp();
+	return m;
+}
+
+/* Level 2: every ray runs the reference's leaf-box test + triangle test over the packet's candidate leaves,
+ * nearest first; a ray stops caring once the entry depth exceeds its culling bound. */
+template <int NR, bool COUNT>
+RTX_DEV void intersect_candidates(const SceneDev &sc, const uint32_t *__restrict__ s_cand, const float *__restrict__ s_key, int ncand,
+                                  const f3 (&d)[NR], uint32_t active, HitRec (&best)[NR], Counters *cnt)
+{
+	const float max_distance = 100000.0f;
+	const f3 o = make_f3(0.0f, 0.0f, 2.0f);
+	f3 id[NR];
+	float cull[NR];
+#pragma unroll
+	for (int r = 0; r < NR; ++r) {
+		id[r] = make_f3(rn_div(1.0f, d[r].x), rn_div(1.0f, d[r].y), rn_div(1.0f, d[r].z));
+		cull[r] = (active >> r) & 1u ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+	}
+	const float abs_margin = 1e-5f * fmaxf(2.0f, sc.scene_scale);
+	unsigned long long visits = 0, tests = 0;
+	for (int k = 0; k < ncand; ++k) {
+		const uint32_t enc = s_cand[k];
+		const float key = s_key[k];                  /* entry depth <= entry parameter of every ray (|(u,v,-1)| >= 1) */
+		uint32_t want = 0;
+#pragma unroll
+		for (int r = 0; r < NR; ++r)
+			if (key < cull[r]) want |= 1u << r;
+		if (!__any_sync(0xffffffffu, want != 0)) break;       /* sorted: nobody wants the rest either */
+		if (want) {
+			const uint32_t first = enc >> 3, count = (enc & 7u) + 1u;
+			for (uint32_t j = 0; j < count; ++j) {
+				const uint32_t tri = first + j;
+				const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+				uint32_t m = 0;
+#pragma unroll
+				for (int r = 0; r < NR; ++r) {
+					if (!((want >> r) & 1u)) continue;
+					if (COUNT) ++visits;
+					const Slab sl = slab_interval<true, 4>(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, o, id[r]);
+					if (sl.tmin <= sl.tmax && sl.tmin < max_distance && sl.tmax > 0.0f) m |= 1u << r;   /* intersect_kernel.cl:41-60 */
+				}
+				if (!m) continue;
+				const float4 *q = sc.tris + 4 * (size_t)tri;
+				const float4 t0 = __ldg(q), t1 = __ldg(q + 1), t2 = __ldg(q + 2), t3 = __ldg(q + 3);
+#pragma unroll
+				for (int r = 0; r < NR; ++r) {
+					if (!((m >> r) & 1u)) continue;
+					TriHit h;
+					if (COUNT) ++tests;
+					if (!triangle_test(t0, t1, t2, t3, o, d[r], cull[r], h)) continue;
+					if (!(h.dist < best[r].dist || (h.dist == best[r].dist && tri < best[r].tri))) continue;
+					best[r].dist = h.dist; best[r].tri = tri; best[r].s = h.s; best[r].t = h.t;
+					cull[r] = h.dist * 1.0001f + abs_margin;
+				}
+			}
+		}
+	}
+	if (COUNT) {
+		atomicAdd(&cnt->leafbox_tests, visits);
+		atomicAdd(&cnt->tri_tests, tests);
+	}
+}
+
 /* Persistent packet kernel: a warp's unit of work is an (8 RX) x (4 RY) pixel block, lane (lx, ly) of the
  * 8 x 4 lane grid owns the RX x RY pixels at (lx RX, ly RY).  32x32 tiles hold 32 / (RX RY) units. */
-template <int BLOCK, int MIN_BLOCKS, int SMEM_STACK, bool COUNT, bool RECORD, int RX, int RY>
+template <int BLOCK, int MIN_BLOCKS, int SMEM_STACK, bool COUNT, bool RECORD, int RX, int RY, bool FRUSTUM>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
 k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 {
@@ -448,6 +651,9 @@ k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	uint2 *s_stack = reinterpret_cast<uint2 *>(smem_raw) + threadIdx.x;
 	const uint32_t lane = threadIdx.x & 31u;
+	/* per-warp candidate list of the frustum front end, after the stacks */
+	uint32_t *s_cand = reinterpret_cast<uint32_t *>(smem_raw + (size_t)SMEM_STACK * BLOCK * sizeof(uint2)) + (threadIdx.x >> 5) * (2 * RTX_CCAP);
+	float *s_key = reinterpret_cast<float *>(s_cand + RTX_CCAP);
 	const f3 o = make_f3(0.0f, 0.0f, 2.0f);
 	for (;;) {
 		uint32_t unit = 0;
@@ -481,9 +687,23 @@ k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 			}
 		}
 		if (!w.ordered_ok) packet = 0;
-		/* all packet rays of the warp in one octant (d.z < 0)?  then the compile-time entry/exit form */
 		const unsigned anyp = __ballot_sync(0xffffffffu, packet != 0);
-		if (anyp) {
+		bool listed = false;
+		if (FRUSTUM && anyp) {
+			const uint32_t *list = w.lists + (size_t)ltile * RTX_LIST_STRIDE;
+			const int n = (int)__ldg(list);
+			if (n >= 0) {
+				const Frustum f = make_frustum(w.cam, (float)(tx * RTX_TILE + (sub % UX) * (8 * RX)), (float)(ty * RTX_TILE + (sub / UX) * (4 * RY)),
+				                               (float)(8 * RX), (float)(4 * RY), sc.scene_scale);
+				const int m = filter_candidates(sc, f, list, n, s_cand, s_key, lane);
+				intersect_candidates<NR, COUNT>(sc, s_cand, s_key, m, d, packet, best, cnt);
+				listed = true;
+			} else if (COUNT && lane == 0) {
+				atomicAdd(&cnt->overflow_packets, 1ull);
+			}
+		}
+		/* all packet rays of the warp in one octant (d.z < 0)?  then the pre-swapped node copy */
+		if (anyp && !listed) {
 			const int src = __ffs(anyp) - 1;
 			const int oct0 = __shfl_sync(0xffffffffu, oct, src);
 			const bool uniform = __all_sync(0xffffffffu, packet == 0 || (same && oct == oct0)) && oct0 < 4;

@@ -26,7 +26,7 @@ NO_HIT = 0xFFFFFFFF
 
 OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NOMEM = range(7)
 
-TUNE_KERNEL, TUNE_LEAF_SIZE, TUNE_RECORD_HITS, TUNE_COUNTERS, TUNE_TOP_SMEM, TUNE_BLOCKS_PER_SM, TUNE_FLATTEN_ON_DEVICE, TUNE_RAYS_PER_THREAD = range(1, 9)
+TUNE_KERNEL, TUNE_LEAF_SIZE, TUNE_RECORD_HITS, TUNE_COUNTERS, TUNE_TOP_SMEM, TUNE_BLOCKS_PER_SM, TUNE_FLATTEN_ON_DEVICE, TUNE_RAYS_PER_THREAD, TUNE_FRUSTUM = range(1, 10)
 KERNEL_PERSISTENT, KERNEL_EXHAUSTIVE = 0, 1
 
 # every symbol include/rtx_b200.h declares (tests check the library exports them all)
@@ -70,6 +70,7 @@ class Stats(C.Structure):
         ("rays", C.c_uint64), ("kernel_ms", C.c_double), ("kernel_launches", C.c_uint32), ("kernel_variant", C.c_uint32),
         ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("leafbox_tests", C.c_uint64),
         ("exact_path_rays", C.c_uint64), ("tree_depth", C.c_uint32), ("num_pairs", C.c_uint32),
+        ("packet_overflows", C.c_uint64),
     ]
 
     def as_dict(self):

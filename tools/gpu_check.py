@@ -46,13 +46,14 @@ def main():
         t = time.time()
         ref = po.render(sc, rt.totalWidth, rt.totalHeight, 1.0, True, want_counters=True)
         print("  oracle: %.2fs  V=%.2f T=%.3f h=%.4f" % (time.time() - t, ref.counters["V"], ref.counters["T"], ref.counters["h"]))
-        for kernel, leaf, top, rpt in ((host.KERNEL_EXHAUSTIVE, 1, 0, 1), (host.KERNEL_PERSISTENT, 1, 0, 1), (host.KERNEL_PERSISTENT, 1, 0, 2),
-                                       (host.KERNEL_PERSISTENT, 1, 0, 4), (host.KERNEL_PERSISTENT, 2, 0, 4), (host.KERNEL_PERSISTENT, 4, 0, 4)):
+        for kernel, leaf, top, rpt, fr in ((host.KERNEL_EXHAUSTIVE, 1, 0, 1, 0), (host.KERNEL_PERSISTENT, 1, 0, 1, 0), (host.KERNEL_PERSISTENT, 1, 0, 4, 0),
+                                           (host.KERNEL_PERSISTENT, 1, 0, 4, 1), (host.KERNEL_PERSISTENT, 4, 0, 4, 1)):
             with host.CudaHost(rt) as hst:
                 hst.set_tunable(host.TUNE_KERNEL, kernel)
                 hst.set_tunable(host.TUNE_LEAF_SIZE, leaf)
                 hst.set_tunable(host.TUNE_TOP_SMEM, top)
                 hst.set_tunable(host.TUNE_RAYS_PER_THREAD, rpt)
+                hst.set_tunable(host.TUNE_FRUSTUM, fr)
                 hst.set_tunable(host.TUNE_RECORD_HITS, 1)
                 hst.set_tunable(host.TUNE_COUNTERS, 1)
                 t = time.time(); hst.upload_scene(sc); t_up = time.time() - t
@@ -60,11 +61,11 @@ def main():
                 st = hst.stats()
                 img = hst.download()
                 fid, dist = hst.download_hits()
-                tag = "%s leaf=%d top=%d rpt=%d" % ("exhaustive" if kernel else "persistent", leaf, top, rpt)
+                tag = "%s leaf=%d rpt=%d frustum=%d" % ("exhaustive" if kernel else "persistent", leaf, rpt, fr)
                 compare(tag, fid, dist, img, ref)
                 rays = st["rays"]
-                print("    counters: visits/ray %.2f tri/ray %.3f leafbox/ray %.3f exact rays %d depth %d pairs %d upload %.1f ms" % (
-                    st["node_visits"] / rays, st["tri_tests"] / rays, st["leafbox_tests"] / rays, st["exact_path_rays"],
+                print("    counters: visits/ray %.2f tri/ray %.3f leafbox/ray %.3f exact rays %d overflow packets %d depth %d pairs %d upload %.1f ms" % (
+                    st["node_visits"] / rays, st["tri_tests"] / rays, st["leafbox_tests"] / rays, st["exact_path_rays"], st["packet_overflows"],
                     st["tree_depth"], st["num_pairs"], t_up * 1e3))
                 hst.set_tunable(host.TUNE_RECORD_HITS, 0)
                 hst.set_tunable(host.TUNE_COUNTERS, 0)
