@@ -64,13 +64,15 @@ struct rtx_ctx {
 	int counters = 0;
 	int top_smem = 0;
 	int blocks_per_sm = 0;       /* 0 = default of the variant */
-	int flatten_on_device = 0;
+	int flatten_on_device = 1;
 	int rays_per_thread = 4;     /* 1, 2 (2x1) or 4 (2x2) pixels per lane */
 	int frustum = -1;            /* frustum front end: 0 off, 1 on, -1 auto (rays per triangle >= 24) */
 	/* scene */
 	bool uploaded = false;
 	SceneDev sc{};
 	DevBuf d_pairs, d_tris, d_leafbox, d_tnormals, d_ref_nodes, d_ref_aabbs;
+	DevBuf t_faces, t_verts, t_vnormals, t_scan;   /* upload staging, kept between uploads */
+	std::vector<uint32_t> h_scan;
 	f3 bbmin{}, bbmax{};
 	uint32_t tree_depth = 0;
 	/* image */
@@ -240,11 +242,11 @@ cudaError_t launch_render_t(rtx_ctx *c, const Work &w, cudaStream_t st, int bloc
 	return cudaGetLastError();
 }
 
-template <int BLOCK, int MINB, int SST, bool COUNT, bool RECORD, int RX, int RY, bool FRUSTUM>
+template <int BLOCK, int MINB, int SST, bool COUNT, bool RECORD, int RX, int RY, int MODE>
 cudaError_t launch_packet_t(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
-	auto k = k_render_packet<BLOCK, MINB, SST, COUNT, RECORD, RX, RY, FRUSTUM>;
-	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2) + (FRUSTUM ? (size_t)(BLOCK / 32) * (2 * RTX_CCAP) * 4 : 0);
+	auto k = k_render_packet<BLOCK, MINB, SST, COUNT, RECORD, RX, RY, MODE>;
+	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2) + (MODE == 1 ? (size_t)(BLOCK / 32) * (2 * RTX_CCAP) * 4 : 0);
 	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	int occ = 0;
@@ -259,9 +261,17 @@ cudaError_t launch_packet_t(rtx_ctx *c, const Work &w, cudaStream_t st)
 template <bool COUNT, bool RECORD>
 cudaError_t launch_packet(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
-	if (c->rays_per_thread == 2) return launch_packet_t<256, 3, 8, COUNT, RECORD, 2, 1, false>(c, w, st);
-	if (w.frustum) return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, true>(c, w, st);
-	return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, false>(c, w, st);
+	if (c->rays_per_thread == 2) return launch_packet_t<256, 3, 8, COUNT, RECORD, 2, 1, 0>(c, w, st);
+	if (w.frustum) {
+		/* listed tiles first (no traversal code in that kernel), then the overflowed ones; both pull
+		 * units from the same kind of counter, so it is re-zeroed in between */
+		cudaError_t e = launch_packet_t<256, 3, 0, COUNT, RECORD, 2, 2, 1>(c, w, st);
+		if (e != cudaSuccess) return e;
+		e = cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st);
+		if (e != cudaSuccess) return e;
+		return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 2>(c, w, st);
+	}
+	return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 0>(c, w, st);
 }
 
 template <bool TOP, bool COUNT, bool RECORD>
@@ -452,7 +462,7 @@ int rtx_create(rtx_ctx **out, const rtx_options *options)
 	if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
 	const size_t out_floats = c->world > 1 ? (size_t)c->tiles_per_rank * RTX_TILE * RTX_TILE : (size_t)c->W * c->H;
 	if ((e = c->d_image.alloc(out_floats * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc(image)");
-	if ((e = c->d_counter.alloc(sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc(counter)");
+	if ((e = c->d_counter.alloc(4 * sizeof(unsigned int))) != cudaSuccess) return bail(e, "cudaMalloc(counter)");
 	if ((e = c->d_counters.alloc(sizeof(Counters))) != cudaSuccess) return bail(e, "cudaMalloc(counters)");
 	if ((e = c->d_sums.alloc(2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc(sums)");
 	if ((e = cudaMemsetAsync(c->d_image.p, 0, out_floats * sizeof(float), c->stream)) != cudaSuccess) return bail(e, "cudaMemset");
@@ -465,7 +475,7 @@ void rtx_destroy(rtx_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
-	DevBuf *bufs[] = { &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
+	DevBuf *bufs[] = { &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
 	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists };
 	for (DevBuf *b : bufs) b->release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
@@ -519,51 +529,84 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 		if (faces[i] >= nverts) return fail(c, RTX_ERR_ARG, "face index out of range");
 	CU(c, cudaSetDevice(c->device));
 	c->uploaded = false;
-
-	Flat flat;
-	flatten(nodes, aabbs16, nnodes, c->leaf_size, c->top_smem > 0 ? (uint32_t)c->top_smem : 0u, flat);
-	/* Octant copies: copy v swaps lo/hi of x (bit 0) and of y (bit 1) in every node, so that a warp whose
-	 * rays all have d.x < 0 (d.y < 0) finds the entry plane in the "lo" slot without a per-box select. */
-	const size_t pair_vecs = flat.pairs.size();
-	flat.pairs.resize(4 * pair_vecs);
-	for (int v = 1; v < 4; ++v) {
-		float4 *dst = flat.pairs.data() + (size_t)v * pair_vecs;
-		for (size_t i = 0; i < pair_vecs; i += 2) {
-			float4 a = flat.pairs[i], b = flat.pairs[i + 1];     /* a = (lo.x lo.y lo.z hi.x), b = (hi.y hi.z ref 0) */
-			if (v & 1) { const float t = a.x; a.x = a.w; a.w = t; }
-			if (v & 2) { const float t = a.y; a.y = b.x; b.x = t; }
-			dst[i] = a;
-			dst[i + 1] = b;
-		}
-	}
-
-	DevBuf d_faces, d_verts, d_vnormals, d_leaf_node;
-	auto cleanup = [&] { d_faces.release(); d_verts.release(); d_vnormals.release(); d_leaf_node.release(); };
-#define CUU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(c, e_, #call); } } while (0)
-	CUU(d_faces.alloc(nfaceidx * 4));
-	CUU(d_verts.alloc(nverts * 16));
-	CUU(d_vnormals.alloc(nverts * 16));
-	CUU(d_leaf_node.alloc(ntris * 4));
+	cudaStream_t st = c->stream;
+	const bool device_flatten = c->flatten_on_device && c->top_smem == 0;
+	size_t num_pairs = 0;
+	uint32_t depth = 0, top_pairs = 0;
+#define CUU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(c, e_, #call); } while (0)
+	CUU(c->t_faces.alloc(nfaceidx * 4));
+	CUU(c->t_verts.alloc(nverts * 16));
+	CUU(c->t_vnormals.alloc(nverts * 16));
 	CUU(c->d_ref_nodes.alloc(nnodes * 4));
 	CUU(c->d_ref_aabbs.alloc(nnodes * 32));
-	CUU(c->d_pairs.alloc(flat.pairs.size() * 16));
 	CUU(c->d_tris.alloc(ntris * 64));
 	CUU(c->d_leafbox.alloc(ntris * 32));
 	CUU(c->d_tnormals.alloc(ntris * 48));
-	cudaStream_t st = c->stream;
-	CUU(cudaMemcpyAsync(d_faces.p, faces, nfaceidx * 4, cudaMemcpyHostToDevice, st));
-	CUU(cudaMemcpyAsync(d_verts.p, verts16, nverts * 16, cudaMemcpyHostToDevice, st));
-	CUU(cudaMemcpyAsync(d_vnormals.p, vnormals16, nverts * 16, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->t_faces.p, faces, nfaceidx * 4, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->t_verts.p, verts16, nverts * 16, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->t_vnormals.p, vnormals16, nverts * 16, cudaMemcpyHostToDevice, st));
 	CUU(cudaMemcpyAsync(c->d_ref_nodes.p, nodes, nnodes * 4, cudaMemcpyHostToDevice, st));
 	CUU(cudaMemcpyAsync(c->d_ref_aabbs.p, aabbs16, nnodes * 32, cudaMemcpyHostToDevice, st));
-	CUU(cudaMemcpyAsync(d_leaf_node.p, flat.leaf_node.data(), ntris * 4, cudaMemcpyHostToDevice, st));
-	CUU(cudaMemcpyAsync(c->d_pairs.p, flat.pairs.data(), flat.pairs.size() * 16, cudaMemcpyHostToDevice, st));
-	k_build_triangles<<<(unsigned)((ntris + 255) / 256), 256, 0, st>>>(
-		d_faces.as<uint32_t>(), d_verts.as<float4>(), d_vnormals.as<float4>(), d_leaf_node.as<uint32_t>(),
-		c->d_ref_aabbs.as<float4>(), (uint32_t)ntris, c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>());
-	CUU(cudaGetLastError());
-	CUU(cudaStreamSynchronize(st));     /* the caller frees its arrays right after (render.cc:96-103) */
-	cleanup();
+	if (device_flatten) {
+		/* one host pass: the two prefix counts k_flatten_nodes needs, and the depth of the flattened tree */
+		std::vector<uint32_t> &scan = c->h_scan;
+		scan.resize(2 * nnodes);
+		uint32_t *first_leaf = scan.data(), *pair_idx = scan.data() + nnodes;
+		std::vector<size_t> ends;          /* pre-order ends of the open internal nodes */
+		uint32_t nl = 0, np = 0;
+		const uint32_t K = (uint32_t)c->leaf_size;
+		for (size_t i = 0; i < nnodes; ++i) {
+			while (!ends.empty() && ends.back() == i) ends.pop_back();
+			first_leaf[i] = nl;
+			pair_idx[i] = np;
+			const uint32_t size = nodes[i];
+			if (size == 1) { ++nl; continue; }
+			if (leaves_of(size) > K || i == 0) {
+				++np;
+				ends.push_back(i + size);
+				if (ends.size() > depth) depth = (uint32_t)ends.size();
+			}
+		}
+		if (nnodes == 1) { np = 1; depth = 1; }
+		num_pairs = np;
+		CUU(c->t_scan.alloc(2 * nnodes * 4));
+		CUU(c->d_pairs.alloc(4 * num_pairs * 64));
+		CUU(cudaMemcpyAsync(c->t_scan.p, scan.data(), 2 * nnodes * 4, cudaMemcpyHostToDevice, st));
+		k_flatten_nodes<<<(unsigned)((nnodes + 255) / 256), 256, 0, st>>>(
+			c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>(), c->t_scan.as<uint32_t>(), c->t_scan.as<uint32_t>() + nnodes,
+			c->t_faces.as<uint32_t>(), c->t_verts.as<float4>(), c->t_vnormals.as<float4>(), (uint32_t)nnodes, (uint32_t)num_pairs, K,
+			c->d_pairs.as<float4>(), c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>());
+		CUU(cudaGetLastError());
+	} else {
+		/* host flatten (needed for the breadth-first prefix that RTX_TUNE_TOP_SMEM stages in shared memory) */
+		Flat flat;
+		flatten(nodes, aabbs16, nnodes, c->leaf_size, c->top_smem > 0 ? (uint32_t)c->top_smem : 0u, flat);
+		const size_t pair_vecs = flat.pairs.size();
+		flat.pairs.resize(4 * pair_vecs);
+		for (int v = 1; v < 4; ++v) {       /* octant copies: swap lo/hi of x (bit 0) and of y (bit 1) */
+			float4 *dst = flat.pairs.data() + (size_t)v * pair_vecs;
+			for (size_t i = 0; i < pair_vecs; i += 2) {
+				float4 a = flat.pairs[i], b = flat.pairs[i + 1];     /* a = (lo.x lo.y lo.z hi.x), b = (hi.y hi.z ref 0) */
+				if (v & 1) { const float t = a.x; a.x = a.w; a.w = t; }
+				if (v & 2) { const float t = a.y; a.y = b.x; b.x = t; }
+				dst[i] = a;
+				dst[i + 1] = b;
+			}
+		}
+		num_pairs = pair_vecs / 4;
+		depth = flat.depth;
+		top_pairs = flat.top_pairs;
+		CUU(c->t_scan.alloc(ntris * 4));
+		CUU(c->d_pairs.alloc(flat.pairs.size() * 16));
+		CUU(cudaMemcpyAsync(c->t_scan.p, flat.leaf_node.data(), ntris * 4, cudaMemcpyHostToDevice, st));
+		CUU(cudaMemcpyAsync(c->d_pairs.p, flat.pairs.data(), flat.pairs.size() * 16, cudaMemcpyHostToDevice, st));
+		k_build_triangles<<<(unsigned)((ntris + 255) / 256), 256, 0, st>>>(
+			c->t_faces.as<uint32_t>(), c->t_verts.as<float4>(), c->t_vnormals.as<float4>(), c->t_scan.as<uint32_t>(),
+			c->d_ref_aabbs.as<float4>(), (uint32_t)ntris, c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>());
+		CUU(cudaGetLastError());
+		CUU(cudaStreamSynchronize(st));     /* flat's vectors die at the end of this block */
+	}
+	CUU(cudaStreamSynchronize(st));         /* the caller frees its arrays right after (render.cc:96-103) */
 #undef CUU
 
 	c->sc.pairs = c->d_pairs.as<float4>();
@@ -572,8 +615,8 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	c->sc.tnormals = c->d_tnormals.as<float4>();
 	c->sc.ref_nodes = c->d_ref_nodes.as<uint32_t>();
 	c->sc.ref_aabbs = c->d_ref_aabbs.as<float4>();
-	c->sc.num_pairs = (uint32_t)(pair_vecs / 4);
-	c->sc.top_pairs = c->top_smem > 0 ? flat.top_pairs : 0;
+	c->sc.num_pairs = (uint32_t)num_pairs;
+	c->sc.top_pairs = c->top_smem > 0 ? top_pairs : 0;
 	c->sc.num_tris = (uint32_t)ntris;
 	c->sc.verify_leafbox = c->leaf_size > 1 ? 1u : 0u;
 	c->bbmin = make_f3(aabbs16[0], aabbs16[1], aabbs16[2]);
@@ -581,8 +624,8 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	float scale = 0.f;
 	for (int k = 0; k < 3; ++k) scale = std::fmax(scale, std::fmax(std::fabs(aabbs16[k]), std::fabs(aabbs16[4 + k])));
 	c->sc.scene_scale = scale;
-	c->tree_depth = flat.depth;
-	c->stats.tree_depth = flat.depth;
+	c->tree_depth = depth;
+	c->stats.tree_depth = depth;
 	c->stats.num_pairs = c->sc.num_pairs;
 	c->uploaded = true;
 	c->rendered = false;
@@ -626,8 +669,9 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	if (w.frustum) {
 		CU(c, c->d_lists.alloc((size_t)c->local_tiles * RTX_LIST_STRIDE * 4));
 		w.lists = c->d_lists.as<uint32_t>();
+		w.overflow_tiles = c->d_counter.as<unsigned int>() + 1;
 	}
-	CU(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
+	CU(c, cudaMemsetAsync(c->d_counter.p, 0, 4 * sizeof(unsigned int), st));
 	if (c->counters) CU(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(Counters), st));
 	CU(c, cudaEventRecord(c->ev0, st));
 	if (w.frustum && c->local_tiles > 0) {
@@ -639,7 +683,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	c->ev_pending = true;
 	c->stats.rays = (uint64_t)c->local_tiles * RTX_TILE * RTX_TILE;
 	if (c->world == 1) c->stats.rays = (uint64_t)c->W * c->H;
-	c->stats.kernel_launches = w.frustum ? 2 : 1;
+	c->stats.kernel_launches = w.frustum ? 3 : 1;
 	c->stats.kernel_variant = (c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
 	c->rendered = true;
 	c->full_valid = false;

@@ -267,6 +267,7 @@ struct Work {
 	int ordered_ok;
 	int frustum;                 /* use the frustum front end for packets */
 	const uint32_t *lists;       /* per-tile candidate lists written by k_frustum_collect */
+	unsigned int *overflow_tiles; /* number of tiles whose list overflowed (zeroed before launch) */
 };
 
 RTX_DEV bool unit_pixel(const Work &w, uint32_t unit, uint32_t lane, uint32_t &x, uint32_t &y, size_t &out)
@@ -534,7 +535,10 @@ k_frustum_collect(const SceneDev sc, const Work w, uint32_t *__restrict__ lists)
 		ncand += nF;
 		__syncwarp();
 	}
-	if (lane == 0) out[0] = (uint32_t)ncand;
+	if (lane == 0) {
+		out[0] = (uint32_t)ncand;
+		if (ncand < 0) atomicAdd(w.overflow_tiles, 1u);
+	}
 	/* rank sort by entry depth (ties by position): the list is short */
 	for (int i = lane; i < ncand; i += 32) {
 		const float ki = s_tkey[i];
@@ -641,10 +645,14 @@ RTX_DEV void intersect_candidates(const SceneDev &sc, const uint32_t *__restrict
 
 /* Persistent packet kernel: a warp's unit of work is an (8 RX) x (4 RY) pixel block, lane (lx, ly) of the
  * 8 x 4 lane grid owns the RX x RY pixels at (lx RX, ly RY).  32x32 tiles hold 32 / (RX RY) units. */
-template <int BLOCK, int MIN_BLOCKS, int SMEM_STACK, bool COUNT, bool RECORD, int RX, int RY, bool FRUSTUM>
+/* MODE 0: per-ray/packet traversal for every tile.
+ * MODE 1: candidate lists only (tiles whose list overflowed are skipped) -- no traversal code in the kernel.
+ * MODE 2: traversal for the tiles MODE 1 skipped; exits at once when k_frustum_collect saw no overflow. */
+template <int BLOCK, int MIN_BLOCKS, int SMEM_STACK, bool COUNT, bool RECORD, int RX, int RY, int MODE>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
 k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 {
+	if (MODE == 2 && *w.overflow_tiles == 0u) return;
 	constexpr int NR = RX * RY;
 	constexpr uint32_t UPT = 32u / NR;                 /* units per tile */
 	constexpr uint32_t UX = RTX_TILE / (8 * RX);       /* units per tile row */
@@ -661,6 +669,11 @@ k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 		unit = __shfl_sync(0xffffffffu, unit, 0);
 		if (unit >= w.local_tiles * UPT) break;
 		const uint32_t ltile = unit / UPT, sub = unit % UPT;
+		int nlist = -1;
+		if (MODE != 0) {
+			nlist = (int)__ldg(w.lists + (size_t)ltile * RTX_LIST_STRIDE);
+			if ((MODE == 1) == (nlist < 0)) continue;       /* MODE 1 takes listed tiles, MODE 2 the overflowed ones */
+		}
 		const uint32_t tile = ltile * w.world + w.rank;
 		const uint32_t tx = tile % w.tiles_x, ty = tile / w.tiles_x;
 		const uint32_t px0 = (sub % UX) * (8 * RX) + (lane & 7u) * RX, py0 = (sub / UX) * (4 * RY) + (lane >> 3) * RY;
@@ -688,22 +701,16 @@ k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 		}
 		if (!w.ordered_ok) packet = 0;
 		const unsigned anyp = __ballot_sync(0xffffffffu, packet != 0);
-		bool listed = false;
-		if (FRUSTUM && anyp) {
-			const uint32_t *list = w.lists + (size_t)ltile * RTX_LIST_STRIDE;
-			const int n = (int)__ldg(list);
-			if (n >= 0) {
+		if (MODE == 1) {
+			if (anyp) {
 				const Frustum f = make_frustum(w.cam, (float)(tx * RTX_TILE + (sub % UX) * (8 * RX)), (float)(ty * RTX_TILE + (sub / UX) * (4 * RY)),
 				                               (float)(8 * RX), (float)(4 * RY), sc.scene_scale);
-				const int m = filter_candidates(sc, f, list, n, s_cand, s_key, lane);
+				const int m = filter_candidates(sc, f, w.lists + (size_t)ltile * RTX_LIST_STRIDE, nlist, s_cand, s_key, lane);
 				intersect_candidates<NR, COUNT>(sc, s_cand, s_key, m, d, packet, best, cnt);
-				listed = true;
-			} else if (COUNT && lane == 0) {
-				atomicAdd(&cnt->overflow_packets, 1ull);
 			}
-		}
-		/* all packet rays of the warp in one octant (d.z < 0)?  then the pre-swapped node copy */
-		if (anyp && !listed) {
+		} else if (anyp) {
+			/* all packet rays of the warp in one octant (d.z < 0)?  then the pre-swapped node copy */
+			if (MODE == 2 && COUNT && lane == 0) atomicAdd(&cnt->overflow_packets, 1ull);
 			const int src = __ffs(anyp) - 1;
 			const int oct0 = __shfl_sync(0xffffffffu, oct, src);
 			const bool uniform = __all_sync(0xffffffffu, packet == 0 || (same && oct == oct0)) && oct0 < 4;
@@ -861,6 +868,88 @@ __global__ void k_deinterleave(const float *__restrict__ gathered, uint32_t worl
 }
 
 /* ------------------- device-side pieces of the flatten ------------------- */
+
+/* The whole flatten in one pass over the reference's pre-order nodes (rtx_upload's default path).
+ * A node is an internal node of the flattened tree iff its subtree holds more than `leaf_size` triangles
+ * (or it is the root); in pre-order its pair index is the number of such nodes before it, and the first
+ * leaf of its subtree is the number of leaves before it -- two prefix counts the host computes while it
+ * validates the arrays.  Internal nodes write their pair (both children) into the four octant copies;
+ * leaves write their triangle record, leaf box and corner normals. */
+__global__ void k_flatten_nodes(const uint32_t *__restrict__ nodes, const float4 *__restrict__ ref_aabbs,
+                                const uint32_t *__restrict__ first_leaf, const uint32_t *__restrict__ pair_idx,
+                                const uint32_t *__restrict__ faces, const float4 *__restrict__ verts,
+                                const float4 *__restrict__ vnormals, uint32_t nnodes, uint32_t num_pairs, uint32_t leaf_size,
+                                float4 *__restrict__ pairs, float4 *__restrict__ tris, float4 *__restrict__ leafbox,
+                                float4 *__restrict__ tnormals)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nnodes) return;
+	const uint32_t size = nodes[i];
+	if (size == 1) {
+		const uint32_t t = first_leaf[i];
+		const uint32_t i0 = faces[3 * (size_t)t], i1 = faces[3 * (size_t)t + 1], i2 = faces[3 * (size_t)t + 2];
+		const float4 A = verts[i0], B = verts[i1], C = verts[i2];
+		const f3 a = make_f3(A.x, A.y, A.z);
+		const f3 u = sub3(make_f3(B.x, B.y, B.z), a);                 /* :68 */
+		const f3 v = sub3(make_f3(C.x, C.y, C.z), a);                 /* :69 */
+		const f3 n = cross3(u, v);                                    /* :70 */
+		const float uu = dot3(u, u), uv = dot3(u, v), vv = dot3(v, v);/* :87-89 */
+		const float D = rn_sub(rn_mul(uv, uv), rn_mul(uu, vv));       /* :93 */
+		float4 *q = tris + 4 * (size_t)t;
+		q[0] = make_float4(a.x, a.y, a.z, n.x);
+		q[1] = make_float4(u.x, u.y, u.z, n.y);
+		q[2] = make_float4(v.x, v.y, v.z, n.z);
+		q[3] = make_float4(uu, uv, vv, D);
+		float4 lo = ref_aabbs[2 * (size_t)i], hi = ref_aabbs[2 * (size_t)i + 1];
+		lo.w = 0.f; hi.w = 0.f;
+		leafbox[2 * (size_t)t] = lo;
+		leafbox[2 * (size_t)t + 1] = hi;
+		float4 n0 = vnormals[i0], n1 = vnormals[i1], n2 = vnormals[i2];
+		n0.w = n1.w = n2.w = 0.f;
+		tnormals[3 * (size_t)t] = n0;
+		tnormals[3 * (size_t)t + 1] = n1;
+		tnormals[3 * (size_t)t + 2] = n2;
+	}
+	if (nnodes == 1) {   /* a single triangle: pair 0 = {the leaf, an unreachable far box} */
+		const float4 lo = ref_aabbs[0], hi = ref_aabbs[1];
+		const int ref = (int)~0u;                                     /* leaf (first 0, count 1) */
+		for (int v = 0; v < 4; ++v) {
+			float4 *p = pairs + 4 * (size_t)v;
+			p[0] = make_float4((v & 1) ? hi.x : lo.x, (v & 2) ? hi.y : lo.y, lo.z, (v & 1) ? lo.x : hi.x);
+			p[1] = make_float4((v & 2) ? lo.y : hi.y, hi.z, __int_as_float(ref), 0.f);
+			p[2] = make_float4(3e38f, 3e38f, 3e38f, 3e38f);
+			p[3] = make_float4(3e38f, 3e38f, __int_as_float(ref), 0.f);
+		}
+		return;
+	}
+	const uint32_t lv = (size + 1) >> 1;
+	if (size == 1 || !(lv > leaf_size || i == 0)) return;
+	const uint32_t p = pair_idx[i];
+	const uint32_t child[2] = { i + 1, i + 1 + nodes[i + 1] };
+	float4 a[2], b[2];
+#pragma unroll
+	for (int k = 0; k < 2; ++k) {
+		const uint32_t c = child[k];
+		const uint32_t clv = (nodes[c] + 1) >> 1;
+		const int ref = clv > leaf_size ? (int)pair_idx[c] : (int)~((first_leaf[c] << 3) | (clv - 1));
+		const float4 lo = ref_aabbs[2 * (size_t)c], hi = ref_aabbs[2 * (size_t)c + 1];
+		a[k] = make_float4(lo.x, lo.y, lo.z, hi.x);
+		b[k] = make_float4(hi.y, hi.z, __int_as_float(ref), 0.f);
+	}
+#pragma unroll
+	for (int v = 0; v < 4; ++v) {       /* octant copies: swap lo/hi of x (bit 0) and of y (bit 1) */
+		float4 *dst = pairs + ((size_t)v * num_pairs + p) * 4;
+#pragma unroll
+		for (int k = 0; k < 2; ++k) {
+			float4 x = a[k], y = b[k];
+			if (v & 1) { const float t = x.x; x.x = x.w; x.w = t; }
+			if (v & 2) { const float t = x.y; x.y = y.x; y.x = t; }
+			dst[2 * k] = x;
+			dst[2 * k + 1] = y;
+		}
+	}
+}
+
 
 /* triangle records, leaf boxes and corner normals from the upload arrays */
 __global__ void k_build_triangles(const uint32_t *__restrict__ faces, const float4 *__restrict__ verts,

@@ -277,6 +277,12 @@ class CudaHost:
         self._ck(self._lib.rtx_get_stats(self._ctx, C.byref(s)))
         return s.as_dict()
 
+    def last_launches(self) -> int:
+        """Kernels launched by the last render / trace call (rtx_stats.kernel_launches)."""
+        s = Stats()
+        self._ck(self._lib.rtx_get_stats(self._ctx, C.byref(s)))
+        return int(s.kernel_launches)
+
     def render_async(self, stream: int = 0):
         self._ck(self._lib.rtx_render_async(self._ctx, C.c_void_p(stream)))
 

@@ -97,7 +97,7 @@ class TiledRenderer:
         torch = self.torch
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.host.render_async(stream)
-        self.kernel_launches += 1
+        self.kernel_launches += self.host.last_launches()
         if self.world > 1:
             self.gathered = gather_to_rank0(self.local, self.world, self.rank)
             if self.rank == 0:
