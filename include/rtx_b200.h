@@ -109,6 +109,7 @@ typedef struct rtx_stats {
 #define RTX_TUNE_FLATTEN_ON_DEVICE 7 /* 1: build the GPU layout with kernels, 0: on the host */
 #define RTX_TUNE_RAYS_PER_THREAD 8 /* primary rays per lane: 1, 2 (2x1 pixels) or 4 (2x2 pixels) */
 #define RTX_TUNE_FRUSTUM       9  /* frustum front end for 16x8-pixel packets: 0 off, 1 on, -1 auto */
+#define RTX_TUNE_LIST_RAYS_PER_THREAD 10 /* rays per lane in the candidate-list kernel: 2 or 4 */
 
 #define RTX_KERNEL_PERSISTENT  0  /* persistent warps, ordered stack traversal, distance culling */
 #define RTX_KERNEL_EXHAUSTIVE  1  /* one thread per ray, the reference's stackless pre-order walk */

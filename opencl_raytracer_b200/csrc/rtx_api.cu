@@ -66,6 +66,7 @@ struct rtx_ctx {
 	int blocks_per_sm = 0;       /* 0 = default of the variant */
 	int flatten_on_device = 1;
 	int rays_per_thread = 4;     /* 1, 2 (2x1) or 4 (2x2) pixels per lane */
+	int list_rays_per_thread = 2; /* rays per lane in the candidate-list kernel: 1, 2 or 4 */
 	int frustum = -1;            /* frustum front end: 0 off, 1 on, -1 auto (rays per triangle >= 24) */
 	/* scene */
 	bool uploaded = false;
@@ -79,7 +80,7 @@ struct rtx_ctx {
 	uint32_t W = 0, H = 0, tiles_x = 0, tiles_y = 0, tiles_per_rank = 0, local_tiles = 0;
 	uint32_t rank = 0, world = 1;
 	float *ext_image = nullptr;  /* caller-owned output (rtx_bind_output) */
-	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums, d_lists;
+	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums, d_lists, d_slists;
 	bool rendered = false, full_valid = false;
 	/* stats */
 	rtx_stats stats{};
@@ -265,7 +266,9 @@ cudaError_t launch_packet(rtx_ctx *c, const Work &w, cudaStream_t st)
 	if (w.frustum) {
 		/* listed tiles first (no traversal code in that kernel), then the overflowed ones; both pull
 		 * units from the same kind of counter, so it is re-zeroed in between */
-		cudaError_t e = launch_packet_t<256, 3, 0, COUNT, RECORD, 2, 2, 1>(c, w, st);
+		cudaError_t e = c->list_rays_per_thread == 1 ? launch_packet_t<256, 5, 0, COUNT, RECORD, 1, 1, 1>(c, w, st)
+		              : c->list_rays_per_thread == 2 ? launch_packet_t<256, 4, 0, COUNT, RECORD, 2, 1, 1>(c, w, st)
+		                                             : launch_packet_t<256, 3, 0, COUNT, RECORD, 2, 2, 1>(c, w, st);
 		if (e != cudaSuccess) return e;
 		e = cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st);
 		if (e != cudaSuccess) return e;
@@ -476,7 +479,7 @@ void rtx_destroy(rtx_ctx *c)
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = { &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
-	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists };
+	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists, &c->d_slists };
 	for (DevBuf *b : bufs) b->release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
@@ -501,6 +504,9 @@ int rtx_set_tunable(rtx_ctx *c, int which, int64_t v)
 		c->top_smem = (int)v; break;
 	case RTX_TUNE_BLOCKS_PER_SM: c->blocks_per_sm = (int)v; break;
 	case RTX_TUNE_FLATTEN_ON_DEVICE: c->flatten_on_device = v != 0; break;
+	case RTX_TUNE_LIST_RAYS_PER_THREAD:
+		if (v != 1 && v != 2 && v != 4) return fail(c, RTX_ERR_ARG, "list rays per thread must be 1, 2 or 4");
+		c->list_rays_per_thread = (int)v; break;
 	case RTX_TUNE_FRUSTUM:
 		if (v < -1 || v > 1) return fail(c, RTX_ERR_ARG, "frustum must be -1, 0 or 1");
 		c->frustum = (int)v; break;
@@ -668,6 +674,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	if (!persistent || c->top_smem > 0) w.frustum = 0;
 	if (w.frustum) {
 		CU(c, c->d_lists.alloc((size_t)c->local_tiles * RTX_LIST_STRIDE * 4));
+		CU(c, c->d_slists.alloc((size_t)((c->tiles_x + RTX_SUPER - 1) / RTX_SUPER) * ((c->tiles_y + RTX_SUPER - 1) / RTX_SUPER) * RTX_SLIST_STRIDE * 4));
 		w.lists = c->d_lists.as<uint32_t>();
 		w.overflow_tiles = c->d_counter.as<unsigned int>() + 1;
 	}
@@ -675,15 +682,24 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	if (c->counters) CU(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(Counters), st));
 	CU(c, cudaEventRecord(c->ev0, st));
 	if (w.frustum && c->local_tiles > 0) {
-		k_frustum_collect<<<(c->local_tiles + 7) / 8, 256, 0, st>>>(c->sc, w, c->d_lists.as<uint32_t>());
+		/* Two levels pay off once there are many tiles: the super-tile pass has the latency of one
+		 * breadth-first walk (~40 us) however few super-tiles there are. */
+		const uint32_t nsuper = ((c->tiles_x + RTX_SUPER - 1) / RTX_SUPER) * ((c->tiles_y + RTX_SUPER - 1) / RTX_SUPER);
+		const bool two_level = c->local_tiles >= 24576;
+		if (two_level) {
+			k_frustum_collect_super<<<(nsuper + 3) / 4, 128, 0, st>>>(c->sc, w, c->d_slists.as<uint32_t>());
+			CU(c, cudaGetLastError());
+		}
+		k_frustum_collect<<<(c->local_tiles + 7) / 8, 256, 0, st>>>(c->sc, w, two_level ? c->d_slists.as<uint32_t>() : nullptr, c->d_lists.as<uint32_t>());
 		CU(c, cudaGetLastError());
+		c->stats.kernel_launches = two_level ? 4 : 3;
 	}
 	CU(c, launch_render(c, w, st));
 	CU(c, cudaEventRecord(c->ev1, st));
 	c->ev_pending = true;
 	c->stats.rays = (uint64_t)c->local_tiles * RTX_TILE * RTX_TILE;
 	if (c->world == 1) c->stats.rays = (uint64_t)c->W * c->H;
-	c->stats.kernel_launches = w.frustum ? 3 : 1;
+	if (!w.frustum) c->stats.kernel_launches = 1;
 	c->stats.kernel_variant = (c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
 	c->rendered = true;
 	c->full_valid = false;

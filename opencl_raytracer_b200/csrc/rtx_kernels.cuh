@@ -484,25 +484,12 @@ RTX_DEV bool frustum_box(float lx, float ly, float lz, float hx, float hy, float
 	       hy >= fminf(ya, yb) - f.margin && ly <= fmaxf(yc, yd) + f.margin;
 }
 
-/* Level 1 kernel: one warp per 32x32-pixel tile walks the tree breadth-first against the tile's frustum,
- * lanes in parallel over the queue, and writes the tile's candidate leaves sorted by entry depth.
- * count = -1: queue or list overflow, the tile's packets use the per-ray traversal. */
-__global__ void __launch_bounds__(256)
-k_frustum_collect(const SceneDev sc, const Work w, uint32_t *__restrict__ lists)
+/* Level 1: a warp walks the tree breadth-first against a frustum, lanes in parallel over the queue, and
+ * writes the candidate leaves sorted by entry depth to out[4..] (codes) and out[4+cap..] (depths).
+ * out[0] = count, or -1 on queue/list overflow. */
+RTX_DEV void collect_frustum(const SceneDev &sc, const Frustum &f, int *__restrict__ s_queue, uint32_t *__restrict__ s_tmp,
+                             float *__restrict__ s_tkey, int cap, uint32_t *__restrict__ out, uint32_t lane, unsigned int *overflow_counter)
 {
-	__shared__ int s_queue_all[8][RTX_QCAP];
-	__shared__ uint32_t s_tmp_all[8][RTX_CCAP];
-	__shared__ float s_tkey_all[8][RTX_CCAP];
-	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-	const uint32_t ltile = blockIdx.x * 8 + warp;
-	if (ltile >= w.local_tiles) return;
-	int *s_queue = s_queue_all[warp];
-	uint32_t *s_tmp = s_tmp_all[warp];
-	float *s_tkey = s_tkey_all[warp];
-	const uint32_t tile = ltile * w.world + w.rank;
-	const uint32_t tx = tile % w.tiles_x, ty = tile / w.tiles_x;
-	const Frustum f = make_frustum(w.cam, (float)(tx * RTX_TILE), (float)(ty * RTX_TILE), (float)RTX_TILE, (float)RTX_TILE, sc.scene_scale);
-	uint32_t *out = lists + (size_t)ltile * RTX_LIST_STRIDE;
 	const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
 	int head = 0, tail = 1, ncand = 0;
 	if (lane == 0) s_queue[0] = 0;
@@ -526,7 +513,7 @@ k_frustum_collect(const SceneDev sc, const Work w, uint32_t *__restrict__ lists)
 		const unsigned bIL = __ballot_sync(full, iL), bIR = __ballot_sync(full, iR);
 		const unsigned bFL = __ballot_sync(full, fL), bFR = __ballot_sync(full, fR);
 		const int nI = __popc(bIL) + __popc(bIR), nF = __popc(bFL) + __popc(bFR);
-		if (tail - head + nI > RTX_QCAP || ncand + nF > RTX_CCAP) { ncand = -1; break; }
+		if (tail - head + nI > RTX_QCAP || ncand + nF > cap) { ncand = -1; break; }
 		if (iL) s_queue[(tail + __popc(bIL & lt)) % RTX_QCAP] = refL;
 		if (iR) s_queue[(tail + __popc(bIL) + __popc(bIR & lt)) % RTX_QCAP] = refR;
 		if (fL) { const int k = ncand + __popc(bFL & lt); s_tmp[k] = ~(uint32_t)refL; s_tkey[k] = eL; }
@@ -537,7 +524,7 @@ k_frustum_collect(const SceneDev sc, const Work w, uint32_t *__restrict__ lists)
 	}
 	if (lane == 0) {
 		out[0] = (uint32_t)ncand;
-		if (ncand < 0) atomicAdd(w.overflow_tiles, 1u);
+		if (ncand < 0 && overflow_counter) atomicAdd(overflow_counter, 1u);
 	}
 	/* rank sort by entry depth (ties by position): the list is short */
 	for (int i = lane; i < ncand; i += 32) {
@@ -548,7 +535,79 @@ k_frustum_collect(const SceneDev sc, const Work w, uint32_t *__restrict__ lists)
 			rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
 		}
 		out[4 + rank] = s_tmp[i];
-		out[4 + RTX_CCAP + rank] = __float_as_uint(ki);
+		out[4 + cap + rank] = __float_as_uint(ki);
+	}
+}
+
+#define RTX_SUPER 4                      /* a super-tile is 4x4 tiles = 128x128 pixels */
+#define RTX_SCAP 384                     /* candidate leaves per super-tile */
+#define RTX_SLIST_STRIDE (2 * RTX_SCAP + 4)
+
+/* Level 1a: one warp per 128x128-pixel super-tile (indexed over the whole image, whatever the rank). */
+__global__ void __launch_bounds__(128)
+k_frustum_collect_super(const SceneDev sc, const Work w, uint32_t *__restrict__ slists)
+{
+	__shared__ int s_queue_all[4][RTX_QCAP];
+	__shared__ uint32_t s_tmp_all[4][RTX_SCAP];
+	__shared__ float s_tkey_all[4][RTX_SCAP];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t stiles_x = (w.tiles_x + RTX_SUPER - 1) / RTX_SUPER, stiles_y = (w.tiles_y + RTX_SUPER - 1) / RTX_SUPER;
+	const uint32_t st = blockIdx.x * 4 + warp;
+	if (st >= stiles_x * stiles_y) return;
+	const uint32_t sx = st % stiles_x, sy = st / stiles_x;
+	const float px = (float)(RTX_TILE * RTX_SUPER);
+	const Frustum f = make_frustum(w.cam, (float)sx * px, (float)sy * px, px, px, sc.scene_scale);
+	collect_frustum(sc, f, s_queue_all[warp], s_tmp_all[warp], s_tkey_all[warp], RTX_SCAP, slists + (size_t)st * RTX_SLIST_STRIDE, lane, nullptr);
+}
+
+/* Level 1b: one warp per 32x32-pixel tile of this rank: filter the super-tile's list with the tile's own
+ * frustum (order preserved); if the super-tile overflowed, walk the tree for the tile itself.
+ * count = -1: the tile's packets use the per-ray traversal. */
+__global__ void __launch_bounds__(256)
+k_frustum_collect(const SceneDev sc, const Work w, const uint32_t *__restrict__ slists, uint32_t *__restrict__ lists)
+{
+	__shared__ int s_queue_all[8][RTX_QCAP];
+	__shared__ uint32_t s_tmp_all[8][RTX_CCAP];
+	__shared__ float s_tkey_all[8][RTX_CCAP];
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint32_t ltile = blockIdx.x * 8 + warp;
+	if (ltile >= w.local_tiles) return;
+	const uint32_t tile = ltile * w.world + w.rank;
+	const uint32_t tx = tile % w.tiles_x, ty = tile / w.tiles_x;
+	const Frustum f = make_frustum(w.cam, (float)(tx * RTX_TILE), (float)(ty * RTX_TILE), (float)RTX_TILE, (float)RTX_TILE, sc.scene_scale);
+	uint32_t *out = lists + (size_t)ltile * RTX_LIST_STRIDE;
+	const uint32_t stiles_x = (w.tiles_x + RTX_SUPER - 1) / RTX_SUPER;
+	const uint32_t *sl = slists ? slists + ((size_t)(ty / RTX_SUPER) * stiles_x + tx / RTX_SUPER) * RTX_SLIST_STRIDE : nullptr;
+	const int n = sl ? (int)__ldg(sl) : -1;             /* no super-tile pass (few tiles): walk the tree per tile */
+	if (n < 0) {
+		collect_frustum(sc, f, s_queue_all[warp], s_tmp_all[warp], s_tkey_all[warp], RTX_CCAP, out, lane, w.overflow_tiles);
+		return;
+	}
+	const unsigned lt = (1u << lane) - 1u;
+	int m = 0;
+	for (int base = 0; base < n; base += 32) {          /* warp-uniform trip count */
+		const int i = base + (int)lane;
+		bool keep = false;
+		uint32_t enc = 0, key = 0;
+		if (i < n) {
+			enc = __ldg(sl + 4 + i);
+			key = __ldg(sl + 4 + RTX_SCAP + i);
+			keep = true;
+			if ((enc & 7u) == 0u) {
+				const uint32_t tri = enc >> 3;
+				const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+				float e;
+				keep = frustum_box(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, f, e);
+			}
+		}
+		const unsigned b = __ballot_sync(0xffffffffu, keep);
+		const int k = m + __popc(b & lt);
+		if (keep && k < RTX_CCAP) { out[4 + k] = enc; out[4 + RTX_CCAP + k] = key; }
+		m += __popc(b);
+	}
+	if (lane == 0) {
+		out[0] = m <= RTX_CCAP ? (uint32_t)m : 0xffffffffu;
+		if (m > RTX_CCAP) atomicAdd(w.overflow_tiles, 1u);
 	}
 }
 

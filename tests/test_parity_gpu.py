@@ -88,6 +88,39 @@ def test_sibenik_standin(po, sibenik_scene, w, h_, ss):
         assert (ref.face_id != host.NO_HIT).mean() > 0.99
 
 
+@pytest.mark.parametrize("list_rpt,leaf", [(1, 1), (2, 1), (4, 1), (2, 4)])
+def test_frustum_front_end_forced(po, bunny_scene, soup_scene, list_rpt, leaf):
+    """The frustum front end forced on: the soup's lists fit, the bunny's fine geometry overflows many tile lists
+    (counted), which exercises the overflow launch; either way every ray equals the oracle."""
+    host = require_gpu()
+    for sc, expect_overflow in ((soup_scene, False), (bunny_scene, True)):
+        rt = host.RayTracer(host.Options(width=300, height=200, nSuperSamples=4))
+        with host.CudaHost(rt) as h:
+            h.set_tunable(host.TUNE_FRUSTUM, 1)
+            h.set_tunable(host.TUNE_LIST_RAYS_PER_THREAD, list_rpt)
+            h.set_tunable(host.TUNE_LEAF_SIZE, leaf)
+            h.set_tunable(host.TUNE_RECORD_HITS, 1)
+            h.set_tunable(host.TUNE_COUNTERS, 1)
+            h.upload_scene(sc)
+            h()
+            check_against_oracle(host, po, sc, rt, h)
+            st = h.stats()
+            assert st["kernel_launches"] >= 3
+            assert (st["packet_overflows"] > 0) == expect_overflow
+            assert st["leafbox_tests"] > 0
+
+
+def test_frustum_auto_rule(po, soup_scene, bunny_scene):
+    """Auto mode: on when the frame has >= 24 rays per triangle (soup: 2400), off otherwise (bunny C1: 20)."""
+    host = require_gpu()
+    for sc, w, expect in ((soup_scene, 600, True), (bunny_scene, 600, False)):
+        rt = host.RayTracer(host.Options(width=w, height=w, nSuperSamples=4))
+        with host.CudaHost(rt) as h:
+            h.upload_scene(sc)
+            h()
+            assert (h.stats()["kernel_launches"] > 1) == expect
+
+
 def test_full_size_properties(po, sibenik_scene):
     """C2 at full size (3840x2160 rays): size-independent properties instead of a full CPU render --
     both kernels agree bit for bit, re-rendering is idempotent, and sampled rows match the oracle."""
