@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="u8", choices=["u8", "float"],
+                    help="what a step ends with on rank 0: the byte image after RayTracer::resize on the device (default; "
+                         "every rank resizes its own tiles, the NCCL gather moves bytes) or the float image (gather moves floats)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -228,7 +231,7 @@ def main():
     # ---------------- value: scene resident, device-timed ----------------
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)                       # kernels, NCCL gather and the events all use this stream
-    r = multigpu.TiledRenderer(rt, sc, rank, world, local_rank)
+    r = multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather=args.gather)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     for _ in range(args.warmup):
         r.render_frame()
@@ -268,13 +271,42 @@ def main():
     parity = None
     if rank == 0:
         from oracle import pyoracle as po
-        img = r.download()
-        step = max(1, th // 24)
-        rows = (step // 3, th, step)
-        ref = po.render(sc, tw, th, 1.0, True, rows=rows, want_ids=False)
-        sel = slice(*rows)
-        parity = {"rows_checked": len(range(*rows)), "pixels_differing": int((img[sel] != ref.image[sel]).sum())}
-        del img
+        n = rt.n
+        ystep = max(1, height // 24)
+        ys = list(range(ystep // 3, height, ystep))             # rows of the final image
+        ref = np.zeros((th, tw), np.float32)
+        for k in range(n):                                       # their n super-sampled rows each
+            ref += po.render(sc, tw, th, 1.0, True, rows=(ys[0] * n + k, th, ystep * n), want_ids=False).image
+        if args.gather == "u8":
+            got = r.download_u8()
+            want = po.resize(ref, width, height, n)
+            parity = {"rows_checked": len(ys), "image": "u8 %dx%d" % (width, height),
+                      "pixels_differing": int((got[ys] != want[ys]).sum())}
+        else:
+            got = r.download()
+            sel = np.concatenate([np.arange(y * n, y * n + n) for y in ys])
+            parity = {"rows_checked": len(sel), "image": "float %dx%d" % (tw, th),
+                      "pixels_differing": int((got[sel] != ref[sel]).sum())}
+        del got, ref
+
+    # N > 1: the same frame with the other gather payload, for comparison
+    other = None
+    if world > 1:
+        alt = "float" if args.gather == "u8" else "u8"
+        r2 = multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather=alt)
+        for _ in range(2):
+            r2.render_frame()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            r2.render_frame()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        tms = torch.tensor([e0.elapsed_time(e1) / 4], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        other = {"gather": alt, "ms_per_step": float(tms.item()), "value": rays / (float(tms.item()) * 1e-3) / 1e6, "unit": "Mrays/s"}
+        r2.close()
 
     # ---------------- e2e: the reference's five calls on host buffers ----------------
     e2e = e2e_u8 = None
@@ -363,9 +395,11 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "scene": sc.name, "triangles": sc.num_triangles, "rays_per_step": rays,
                        "parallelism": "interleaved 32x32 tiles over %d GPU(s), scene replicated, 1 NCCL gather/frame" % world,
+                       "step": "trace + RayTracer::resize on the device%s -> %s image on rank 0" % (
+                           " + 1 NCCL gather + de-interleave" if world > 1 else "", "byte" if args.gather == "u8" else "float"),
                        "l2": "flushed between timed iterations (256 MiB memset, untimed)"},
             "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(lt.item()),
-            "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity,
+            "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "other_gather": other,
             "step_ms": [float(x) for x in step_ms],
         }))
     if world > 1:

@@ -203,6 +203,13 @@ int rtx_probe_bandwidth(rtx_ctx *ctx, int level, size_t bytes, int iters, double
 int rtx_tile_layout(uint32_t total_width, uint32_t total_height, uint32_t world,
                     uint32_t *tiles_x, uint32_t *tiles_y, uint32_t *tiles_per_rank);
 
+/* Byte path (needs sqrt(n_super_samples) to divide 32 when tile_world > 1): RayTracer::resize on this
+ * context's share.  tile_world <= 1: into the context's byte image (d_tiles_u8 ignored).  Otherwise into
+ * the caller's compact buffer of tiles_per_rank * (32/n)^2 bytes, to be gathered and handed to
+ * rtx_deinterleave_u8_async on rank 0.  rtx_download_u8 then returns the width*height bytes. */
+int rtx_resize_u8_async(rtx_ctx *ctx, void *d_tiles_u8, size_t count, void *stream);
+int rtx_deinterleave_u8_async(rtx_ctx *ctx, const void *d_gathered_u8, uint32_t world, void *stream);
+
 /* Scatter `world` gathered compact buffers (rank-major, tiles_per_rank*1024
  * floats each) into the row-major image of this context (rank 0). */
 int rtx_deinterleave_async(rtx_ctx *ctx, const void *d_gathered, uint32_t world, void *stream);

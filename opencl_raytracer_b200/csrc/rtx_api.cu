@@ -81,7 +81,7 @@ struct rtx_ctx {
 	uint32_t rank = 0, world = 1;
 	float *ext_image = nullptr;  /* caller-owned output (rtx_bind_output) */
 	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums, d_lists, d_slists;
-	bool rendered = false, full_valid = false;
+	bool rendered = false, full_valid = false, u8_valid = false;
 	/* stats */
 	rtx_stats stats{};
 };
@@ -703,6 +703,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	c->stats.kernel_variant = (c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
 	c->rendered = true;
 	c->full_valid = false;
+	c->u8_valid = false;
 	return RTX_OK;
 }
 
@@ -790,9 +791,60 @@ int rtx_download_hits(rtx_ctx *c, uint32_t *face_id, float *distance)
 	return RTX_OK;
 }
 
+static uint32_t super_n(const rtx_ctx *c) { return (uint32_t)std::sqrt((double)c->opt.n_super_samples); }
+
+int rtx_resize_u8_async(rtx_ctx *c, void *d_tiles_u8, size_t count, void *stream)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (!c->rendered) return fail(c, RTX_ERR_STATE, "resize before render");
+	const uint32_t n = super_n(c), w = c->opt.width, h = c->opt.height;
+	if (n == 0 || (uint64_t)w * n > c->W || (uint64_t)h * n > c->H) return fail(c, RTX_ERR_ARG, "image smaller than width*n x height*n");
+	CU(c, cudaSetDevice(c->device));
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (c->world == 1) {
+		CU(c, c->d_u8.alloc((size_t)w * h));
+		const float *src = c->ext_image ? c->ext_image : c->d_image.as<float>();
+		const dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+		k_resize_u8<<<grid, block, 0, st>>>(src, c->W, w, h, n, c->d_u8.as<unsigned char>());
+		CU(c, cudaGetLastError());
+		c->u8_valid = true;
+		return RTX_OK;
+	}
+	if (RTX_TILE % n != 0) return fail(c, RTX_ERR_UNSUPPORTED, "per-rank resize needs sqrt(n_super_samples) to divide 32; gather floats instead");
+	const uint32_t m = RTX_TILE / n;
+	const size_t need = (size_t)c->tiles_per_rank * m * m;
+	if (!d_tiles_u8 || count < need) return fail(c, RTX_ERR_ARG, "u8 tile buffer too small");
+	const float *src = c->ext_image ? c->ext_image : c->d_image.as<float>();
+	k_resize_tiles_u8<<<(unsigned)((need + 255) / 256), 256, 0, st>>>(src, c->tiles_per_rank, n, static_cast<unsigned char *>(d_tiles_u8));
+	CU(c, cudaGetLastError());
+	return RTX_OK;
+}
+
+int rtx_deinterleave_u8_async(rtx_ctx *c, const void *d_gathered, uint32_t world, void *stream)
+{
+	if (!c || !d_gathered || world == 0) return fail(c, RTX_ERR_ARG, "null argument");
+	const uint32_t n = super_n(c);
+	if (n == 0 || RTX_TILE % n != 0) return fail(c, RTX_ERR_UNSUPPORTED, "sqrt(n_super_samples) must divide 32");
+	CU(c, cudaSetDevice(c->device));
+	CU(c, c->d_u8.alloc((size_t)c->opt.width * c->opt.height));
+	uint32_t tx, ty, tpr;
+	rtx_tile_layout(c->W, c->H, world, &tx, &ty, &tpr);
+	k_deinterleave_u8<<<tx * ty, 64, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned char *>(d_gathered), world, tpr, tx, ty, n,
+	                                                                          c->opt.width, c->opt.height, c->d_u8.as<unsigned char>());
+	CU(c, cudaGetLastError());
+	c->u8_valid = true;
+	return RTX_OK;
+}
+
 int rtx_download_u8(rtx_ctx *c, unsigned char *image)
 {
 	if (!c || !image) return fail(c, RTX_ERR_ARG, "null argument");
+	if (c->u8_valid) {          /* already resized on the device (rtx_resize_u8_async / rtx_deinterleave_u8_async) */
+		CU(c, cudaSetDevice(c->device));
+		CU(c, cudaDeviceSynchronize());
+		CU(c, cudaMemcpy(image, c->d_u8.p, (size_t)c->opt.width * c->opt.height, cudaMemcpyDeviceToHost));
+		return RTX_OK;
+	}
 	const float *src = full_image(c);
 	if (!src || (!c->rendered && !c->full_valid)) return fail(c, RTX_ERR_STATE, "no complete image on this context");
 	const uint32_t n = (uint32_t)std::sqrt((double)c->opt.n_super_samples);

@@ -910,6 +910,39 @@ __global__ void k_resize_u8(const float *__restrict__ img, uint32_t total_width,
 	out[(size_t)y * width + x] = (unsigned char)(int)v;
 }
 
+/* RayTracer::resize on a rank's compact tiles: [ltile][32][32] floats -> [ltile][32/n][32/n] bytes (n divides 32,
+ * so no output pixel straddles tiles or ranks).  Same summation order as k_resize_u8. */
+__global__ void k_resize_tiles_u8(const float *__restrict__ tiles, uint32_t ntiles, uint32_t n, unsigned char *__restrict__ out)
+{
+	const uint32_t m = RTX_TILE / n;                 /* output pixels per tile side */
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (size_t)ntiles * m * m) return;
+	const uint32_t t = (uint32_t)(i / (m * m)), r = (uint32_t)(i % (m * m)), oy = r / m, ox = r % m;
+	const float *src = tiles + (size_t)t * (RTX_TILE * RTX_TILE);
+	float total = 0.0f;
+	for (uint32_t sy = 0; sy < n; ++sy)
+		for (uint32_t sx = 0; sx < n; ++sx)
+			total = rn_add(total, src[(oy * n + sy) * RTX_TILE + (ox * n + sx)]);
+	out[i] = (unsigned char)(int)rn_mul(rn_div(total, (float)(n * n)), 255.0f);
+}
+
+/* rank-major gathered compact u8 tiles -> row-major width x height byte image (rank 0) */
+__global__ void k_deinterleave_u8(const unsigned char *__restrict__ gathered, uint32_t world, uint32_t tiles_per_rank,
+                                  uint32_t tiles_x, uint32_t tiles_y, uint32_t n, uint32_t width, uint32_t height,
+                                  unsigned char *__restrict__ image)
+{
+	const uint32_t tile = blockIdx.x;
+	if (tile >= tiles_x * tiles_y) return;
+	const uint32_t m = RTX_TILE / n;
+	const uint32_t rank = tile % world, ltile = tile / world;
+	const unsigned char *src = gathered + ((size_t)rank * tiles_per_rank + ltile) * (m * m);
+	const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+	for (uint32_t i = threadIdx.x; i < m * m; i += blockDim.x) {
+		const uint32_t x = tx * m + i % m, y = ty * m + i / m;
+		if (x < width && y < height) image[(size_t)y * width + x] = src[i];
+	}
+}
+
 /* rank-major gathered compact tile buffers -> row-major image (rank 0) */
 __global__ void k_deinterleave(const float *__restrict__ gathered, uint32_t world, uint32_t tiles_per_rank,
                                uint32_t tiles_x, uint32_t tiles_y, uint32_t W, uint32_t H, float *__restrict__ image)

@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "rtx_download", "rtx_destroy", "rtx_last_error", "rtx_set_tunable", "rtx_get_stats", "rtx_render_async",
     "rtx_synchronize", "rtx_download_hits", "rtx_download_u8", "rtx_device_image", "rtx_trace_rays",
     "rtx_trace_rays_device", "rtx_trace_random_rays", "rtx_tile_layout", "rtx_deinterleave_async", "rtx_bind_output",
-    "rtx_probe_bandwidth",
+    "rtx_probe_bandwidth", "rtx_resize_u8_async", "rtx_deinterleave_u8_async",
 )
 
 
@@ -122,6 +122,10 @@ def load_library():
     lib.rtx_device_image.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     lib.rtx_bind_output.restype = C.c_int
     lib.rtx_bind_output.argtypes = [vp, vp, C.c_size_t]
+    lib.rtx_resize_u8_async.restype = C.c_int
+    lib.rtx_resize_u8_async.argtypes = [vp, vp, C.c_size_t, vp]
+    lib.rtx_deinterleave_u8_async.restype = C.c_int
+    lib.rtx_deinterleave_u8_async.argtypes = [vp, vp, C.c_uint32, vp]
     lib.rtx_probe_bandwidth.restype = C.c_int
     lib.rtx_probe_bandwidth.argtypes = [vp, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     lib.rtx_trace_rays.restype = C.c_int
@@ -338,6 +342,12 @@ class CudaHost:
                                                  dist.ctypes.data if want_arrays else None,
                                                  C.byref(hits), C.byref(idsum)))
         return hits.value, idsum.value, fid, dist
+
+    def resize_u8_async(self, d_tiles_u8: int = 0, count: int = 0, stream: int = 0):
+        self._ck(self._lib.rtx_resize_u8_async(self._ctx, C.c_void_p(d_tiles_u8), count, C.c_void_p(stream)))
+
+    def deinterleave_u8_async(self, d_gathered: int, world: int, stream: int = 0):
+        self._ck(self._lib.rtx_deinterleave_u8_async(self._ctx, C.c_void_p(d_gathered), world, C.c_void_p(stream)))
 
     def deinterleave_async(self, d_gathered: int, world: int, stream: int = 0):
         self._ck(self._lib.rtx_deinterleave_async(self._ctx, C.c_void_p(d_gathered), world, C.c_void_p(stream)))

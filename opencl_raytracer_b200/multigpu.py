@@ -79,11 +79,17 @@ class TiledRenderer:
         img = r.download()              # rank 0 only
     """
 
-    def __init__(self, rt, scene, rank: int, world: int, device: int, jitter_seed: int = 0):
+    def __init__(self, rt, scene, rank: int, world: int, device: int, jitter_seed: int = 0, gather: str = "float"):
+        """gather = "float": the frame's collective moves the float tiles (what ``download(float*)`` needs);
+        gather = "u8": every rank applies RayTracer::resize to its own tiles first and the collective moves
+        bytes -- (n*n*4)x less traffic into rank 0; needs sqrt(nSuperSamples) to divide 32."""
         import torch
         from . import host
         self.torch = torch
         self.rank, self.world, self.rt = rank, world, rt
+        self.gather = gather
+        if gather == "u8" and world > 1 and TILE % rt.n != 0:
+            raise ValueError("u8 gather needs sqrt(nSuperSamples) to divide %d" % TILE)
         self.dev = torch.device("cuda", device)
         self.host = host.CudaHost(rt, device=device, jitter_seed=jitter_seed, tile_rank=rank, tile_world=world)
         self.host.upload_scene(scene)
@@ -92,13 +98,27 @@ class TiledRenderer:
         self.host.bind_output(self.local.data_ptr(), n)
         self.gathered = None
         self.kernel_launches = 0
+        if gather == "u8" and world > 1:
+            m = TILE // rt.n
+            self.local_u8 = torch.zeros(tile_counts(rt.totalWidth, rt.totalHeight, world)[2] * m * m, dtype=torch.uint8, device=self.dev)
 
     def render_frame(self):
         torch = self.torch
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.host.render_async(stream)
         self.kernel_launches += self.host.last_launches()
-        if self.world > 1:
+        if self.gather == "u8":
+            if self.world == 1:
+                self.host.resize_u8_async(0, 0, stream)
+                self.kernel_launches += 1
+            else:
+                self.host.resize_u8_async(self.local_u8.data_ptr(), self.local_u8.numel(), stream)
+                self.kernel_launches += 1
+                self.gathered = gather_to_rank0(self.local_u8, self.world, self.rank)
+                if self.rank == 0:
+                    self.host.deinterleave_u8_async(self.gathered.data_ptr(), self.world, stream)
+                    self.kernel_launches += 1
+        elif self.world > 1:
             self.gathered = gather_to_rank0(self.local, self.world, self.rank)
             if self.rank == 0:
                 self.host.deinterleave_async(self.gathered.data_ptr(), self.world, stream)

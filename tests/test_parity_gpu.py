@@ -293,6 +293,16 @@ def test_tile_partition_equals_single_image(po, soup_scene, world):
         ctxs[0].synchronize()
         assert np.array_equal(ctxs[0].download(), single)
         assert np.array_equal(ctxs[0].download_u8(), single_u8)
+        # byte path: every rank resizes its own tiles, the gather moves (32/n)^2 bytes per tile
+        m = 32 // rt.n
+        gathered_u8 = torch.zeros(world * tpr * m * m, dtype=torch.uint8, device="cuda")
+        for r, c in enumerate(ctxs):
+            c()
+            c.resize_u8_async(gathered_u8[r * tpr * m * m:(r + 1) * tpr * m * m].data_ptr(), tpr * m * m)
+            c.synchronize()
+        ctxs[0].deinterleave_u8_async(gathered_u8.data_ptr(), world)
+        ctxs[0].synchronize()
+        assert np.array_equal(ctxs[0].download_u8(), single_u8)
     finally:
         for c in ctxs:
             c.close()
