@@ -107,9 +107,10 @@ typedef struct rtx_stats {
 #define RTX_TUNE_TOP_SMEM      5  /* node pairs of the top levels staged in shared memory, 0 = off */
 #define RTX_TUNE_BLOCKS_PER_SM 6
 #define RTX_TUNE_FLATTEN_ON_DEVICE 7 /* 1: build the GPU layout with kernels, 0: on the host */
-#define RTX_TUNE_RAYS_PER_THREAD 8 /* primary rays per lane: 1, 2 (2x1 pixels) or 4 (2x2 pixels) */
+#define RTX_TUNE_RAYS_PER_THREAD 8 /* primary rays per lane in the traversal kernel: 1, 2 (2x1 pixels), 4 (2x2 pixels), or 0 = the refill kernel */
 #define RTX_TUNE_FRUSTUM       9  /* frustum front end for 16x8-pixel packets: 0 off, 1 on, -1 auto */
-#define RTX_TUNE_LIST_RAYS_PER_THREAD 10 /* rays per lane in the candidate-list kernel: 2 or 4 */
+#define RTX_TUNE_LIST_RAYS_PER_THREAD 10 /* rays per lane in the candidate-list kernel: 1, 2 or 4 */
+#define RTX_TUNE_INCOHERENT_KERNEL 11 /* arbitrary rays: 1 persistent refill + parked leaves (default), 0 plain while-while */
 
 #define RTX_KERNEL_PERSISTENT  0  /* persistent warps, ordered stack traversal, distance culling */
 #define RTX_KERNEL_EXHAUSTIVE  1  /* one thread per ray, the reference's stackless pre-order walk */

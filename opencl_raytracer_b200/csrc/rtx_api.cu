@@ -65,8 +65,9 @@ struct rtx_ctx {
 	int top_smem = 0;
 	int blocks_per_sm = 0;       /* 0 = default of the variant */
 	int flatten_on_device = 1;
-	int rays_per_thread = 4;     /* 1, 2 (2x1) or 4 (2x2) pixels per lane */
+	int rays_per_thread = 1;     /* traversal kernel: 1, 2 (2x1) or 4 (2x2) pixels per lane, 0 = refill kernel */
 	int list_rays_per_thread = 2; /* rays per lane in the candidate-list kernel: 1, 2 or 4 */
+	int incoherent_kernel = 1;   /* 1: persistent refill + parked leaves for arbitrary rays, 0: plain while-while */
 	int frustum = -1;            /* frustum front end: 0 off, 1 on, -1 auto (rays per triangle >= 24) */
 	/* scene */
 	bool uploaded = false;
@@ -243,6 +244,23 @@ cudaError_t launch_render_t(rtx_ctx *c, const Work &w, cudaStream_t st, int bloc
 	return cudaGetLastError();
 }
 
+template <bool COUNT, bool RECORD, int SOURCE>
+cudaError_t launch_pt(rtx_ctx *c, const RayWork &rw, const Work &pw, cudaStream_t st)
+{
+	constexpr int BLOCK = 256, MINB = 3, SST = 8;
+	auto k = k_trace_persistent<BLOCK, MINB, SST, COUNT, RECORD, SOURCE>;
+	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2);
+	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	int occ = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BLOCK, smem);
+	if (e != cudaSuccess) return e;
+	if (occ < 1) occ = 1;
+	if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
+	k<<<(unsigned)(c->sm_count * occ), BLOCK, smem, st>>>(c->sc, rw, pw, c->d_counters.as<Counters>());
+	return cudaGetLastError();
+}
+
 template <int BLOCK, int MINB, int SST, bool COUNT, bool RECORD, int RX, int RY, int MODE>
 cudaError_t launch_packet_t(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
@@ -262,7 +280,7 @@ cudaError_t launch_packet_t(rtx_ctx *c, const Work &w, cudaStream_t st)
 template <bool COUNT, bool RECORD>
 cudaError_t launch_packet(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
-	if (c->rays_per_thread == 2) return launch_packet_t<256, 3, 8, COUNT, RECORD, 2, 1, 0>(c, w, st);
+	if (c->rays_per_thread == 2 && !w.frustum) return launch_packet_t<256, 3, 8, COUNT, RECORD, 2, 1, 0>(c, w, st);
 	if (w.frustum) {
 		/* listed tiles first (no traversal code in that kernel), then the overflowed ones; both pull
 		 * units from the same kind of counter, so it is re-zeroed in between */
@@ -295,7 +313,12 @@ cudaError_t launch_render(rtx_ctx *c, const Work &w, cudaStream_t st)
 		           else k_render_exhaustive<false, false><<<grid, 256, 0, st>>>(c->sc, w, c->d_counters.as<Counters>()); }
 		return cudaGetLastError();
 	}
-	if (c->rays_per_thread > 1 && !top) {
+	if (c->rays_per_thread == 0 && !top && !w.frustum && (uint64_t)w.num_units * 32ull < 0xfff00000ull) {      /* persistent refill kernel on primary rays */
+		RayWork none{};
+		if (cnt) return rec ? launch_pt<true, true, 1>(c, none, w, st) : launch_pt<true, false, 1>(c, none, w, st);
+		return rec ? launch_pt<false, true, 1>(c, none, w, st) : launch_pt<false, false, 1>(c, none, w, st);
+	}
+	if ((w.frustum || c->rays_per_thread > 1) && !top) {
 		if (cnt) return rec ? launch_packet<true, true>(c, w, st) : launch_packet<true, false>(c, w, st);
 		return rec ? launch_packet<false, true>(c, w, st) : launch_packet<false, false>(c, w, st);
 	}
@@ -328,6 +351,10 @@ cudaError_t launch_rays_t(rtx_ctx *c, const RayWork &w, cudaStream_t st)
 cudaError_t launch_rays(rtx_ctx *c, const RayWork &w, cudaStream_t st)
 {
 	const bool top = c->top_smem > 0 && c->sc.top_pairs > 0, cnt = c->counters != 0;
+	if (c->incoherent_kernel && !top) {
+		Work none{};
+		return cnt ? launch_pt<true, false, 0>(c, w, none, st) : launch_pt<false, false, 0>(c, w, none, st);
+	}
 	if (top) return cnt ? launch_rays_t<true, true>(c, w, st) : launch_rays_t<true, false>(c, w, st);
 	return cnt ? launch_rays_t<false, true>(c, w, st) : launch_rays_t<false, false>(c, w, st);
 }
@@ -507,11 +534,12 @@ int rtx_set_tunable(rtx_ctx *c, int which, int64_t v)
 	case RTX_TUNE_LIST_RAYS_PER_THREAD:
 		if (v != 1 && v != 2 && v != 4) return fail(c, RTX_ERR_ARG, "list rays per thread must be 1, 2 or 4");
 		c->list_rays_per_thread = (int)v; break;
+	case RTX_TUNE_INCOHERENT_KERNEL: c->incoherent_kernel = v != 0; break;
 	case RTX_TUNE_FRUSTUM:
 		if (v < -1 || v > 1) return fail(c, RTX_ERR_ARG, "frustum must be -1, 0 or 1");
 		c->frustum = (int)v; break;
 	case RTX_TUNE_RAYS_PER_THREAD:
-		if (v != 1 && v != 2 && v != 4) return fail(c, RTX_ERR_ARG, "rays per thread must be 1, 2 or 4");
+		if (v != 0 && v != 1 && v != 2 && v != 4) return fail(c, RTX_ERR_ARG, "rays per thread must be 0 (refill kernel), 1, 2 or 4");
 		c->rays_per_thread = (int)v; break;
 	default: return fail(c, RTX_ERR_ARG, "unknown tunable");
 	}
@@ -669,7 +697,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	w.ordered_ok = c->tree_depth <= RTX_STACK_MAX ? 1 : 0;
 	/* frustum front end pays off when packets see few triangles: many rays per triangle */
 	const double rays_per_tri = (double)c->W * c->H / (double)c->sc.num_tris;
-	w.frustum = (c->frustum == 1 || (c->frustum < 0 && rays_per_tri >= 24.0)) && c->rays_per_thread == 4 && w.ordered_ok ? 1 : 0;
+	w.frustum = (c->frustum == 1 || (c->frustum < 0 && rays_per_tri >= 24.0)) && w.ordered_ok ? 1 : 0;
 	const bool persistent = !(c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok);
 	if (!persistent || c->top_smem > 0) w.frustum = 0;
 	if (w.frustum) {
@@ -685,7 +713,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 		/* Two levels pay off once there are many tiles: the super-tile pass has the latency of one
 		 * breadth-first walk (~40 us) however few super-tiles there are. */
 		const uint32_t nsuper = ((c->tiles_x + RTX_SUPER - 1) / RTX_SUPER) * ((c->tiles_y + RTX_SUPER - 1) / RTX_SUPER);
-		const bool two_level = c->local_tiles >= 24576;
+		const bool two_level = c->local_tiles >= 10000;
 		if (two_level) {
 			k_frustum_collect_super<<<(nsuper + 3) / 4, 128, 0, st>>>(c->sc, w, c->d_slists.as<uint32_t>());
 			CU(c, cudaGetLastError());
@@ -882,7 +910,7 @@ int rtx_trace_rays_device(rtx_ctx *c, const void *d_origins, const void *d_dirs,
 	if (!c->uploaded) return fail(c, RTX_ERR_STATE, "trace before upload");
 	if (nrays == 0) return RTX_OK;
 	if (!d_origins || !d_dirs) return fail(c, RTX_ERR_ARG, "null ray arrays");
-	if (nrays >= (1ull << 36)) return fail(c, RTX_ERR_ARG, "too many rays in one call");
+	if (nrays >= 0xfff00000ull) return fail(c, RTX_ERR_ARG, "too many rays in one call (limit 2^32 - 2^20)");
 	CU(c, cudaSetDevice(c->device));
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	RayWork w{};
@@ -949,7 +977,7 @@ int rtx_trace_random_rays(rtx_ctx *c, uint32_t seed, uint64_t first, size_t nray
 	if (hit_count) *hit_count = 0;
 	if (sum_face_id) *sum_face_id = 0;
 	if (nrays == 0) return RTX_OK;
-	if (nrays >= (1ull << 36)) return fail(c, RTX_ERR_ARG, "too many rays in one call");
+	if (nrays >= 0xfff00000ull) return fail(c, RTX_ERR_ARG, "too many rays in one call (limit 2^32 - 2^20)");
 	CU(c, cudaSetDevice(c->device));
 	if (face_id) CU(c, c->d_face_id.alloc(nrays * 4));
 	if (distance) CU(c, c->d_dist.alloc(nrays * 4));

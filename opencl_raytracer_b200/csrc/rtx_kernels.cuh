@@ -893,6 +893,212 @@ k_trace_rays(const SceneDev sc, const RayWork w, Counters *cnt)
 	}
 }
 
+/* --------------------------------------------------------------------------
+ * Persistent traversal for rays that are NOT coherent (arbitrary / random rays, primary rays over geometry
+ * finer than the pixel grid).  ncu on the while-while kernel with random rays (profiles/r1_c5_*): 5.1 of 32
+ * lanes active on average, 1.3 in the triangle test -- every lane reaches its leaves at a different time and
+ * finished rays leave their lane idle.  Here a warp keeps its lanes busy in three warp-synchronous phases:
+ *   fetch    when fewer than RTX_PT_REFILL lanes still own a ray, the idle lanes pull new rays from the
+ *            global counter (one atomicAdd per warp, __ballot_sync/__popc to hand them out);
+ *   descend  lanes with an interior node test its two children; a lane that reaches a leaf parks it as
+ *            "pending" and keeps descending from its stack (speculative traversal) until it meets a second
+ *            leaf; the phase ends when fewer than RTX_PT_MIN_DESCEND lanes still descend;
+ *   leaves   all lanes with a pending leaf run the triangle tests together.
+ * Per ray the tests, the acceptance rule and the culling bound are those of traverse_ordered; a parked
+ * leaf is merely tested a little later, against a bound that can only have become tighter.
+ * ------------------------------------------------------------------------ */
+#define RTX_PT_REFILL 20
+#define RTX_PT_MIN_DESCEND 12
+#define RTX_PT_DONE ((int)0x80000000)
+#define RTX_PT_NONE ((int)0x80000001)
+
+struct PtRay {
+	f3 o, d, id;
+	float max_distance, inv_len, abs_margin, cull, limit;
+	HitRec best;
+	int cur, pend, sp;
+	unsigned long long index;
+};
+
+template <int SMEM_STACK>
+RTX_DEV int pt_pop(PtRay &r, const uint2 *__restrict__ s_stack, const uint2 *l_stack, int stride)
+{
+	while (r.sp > 0) {
+		--r.sp;
+		const uint2 e = (SMEM_STACK > 0 && r.sp < SMEM_STACK) ? s_stack[r.sp * stride] : l_stack[r.sp - SMEM_STACK];
+		if (__uint_as_float(e.y) < r.limit) return (int)e.x;
+	}
+	return RTX_PT_DONE;
+}
+
+/* SOURCE 0: rays from arrays or from the counter-based generator (RayWork); SOURCE 1: primary rays (Work). */
+template <int BLOCK, int MIN_BLOCKS, int SMEM_STACK, bool COUNT, bool RECORD, int SOURCE>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
+k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters *cnt)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	uint2 *s_stack = reinterpret_cast<uint2 *>(smem_raw) + threadIdx.x;
+	const int stride = blockDim.x;
+	uint2 l_stack[RTX_STACK_MAX - SMEM_STACK];
+	const uint32_t lane = threadIdx.x & 31u;
+	const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+	const unsigned long long total = SOURCE == 0 ? rw.nrays : (unsigned long long)pw.num_units * 32ull;
+	unsigned int *counter = SOURCE == 0 ? rw.counter : pw.counter;
+	const bool ordered_ok = SOURCE == 0 ? (rw.ordered_ok != 0 && !rw.exhaustive) : pw.ordered_ok != 0;
+	unsigned long long hits = 0, idsum = 0, visits = 0, tests = 0, lbtests = 0;
+	PtRay r;
+	bool has_ray = false, exhausted = false;
+	r.cur = RTX_PT_DONE; r.pend = RTX_PT_NONE; r.sp = 0;
+
+	for (;;) {
+		/* ---------------- fetch ---------------- */
+		const unsigned idle = __ballot_sync(full, !has_ray);
+		if (!exhausted && __popc(idle) >= 32 - RTX_PT_REFILL + 1) {
+			unsigned long long base = 0;
+			const int want = __popc(idle);
+			if (lane == 0) base = (unsigned long long)atomicAdd(counter, (unsigned int)want);
+			base = __shfl_sync(full, base, 0);
+			if (base + want >= total) exhausted = true;
+			if (!has_ray) {
+				const unsigned long long idx = base + __popc(idle & lt);
+				if (idx < total) {
+					bool valid = true;
+					size_t out = 0;
+					if (SOURCE == 0) {
+						if (rw.origins) {
+							const float4 oo = __ldg(rw.origins + idx), dd = __ldg(rw.dirs + idx);
+							r.o = make_f3(oo.x, oo.y, oo.z);
+							r.d = make_f3(dd.x, dd.y, dd.z);
+						} else {
+							random_ray(rw.seed, rw.first + idx, rw.bbmin, rw.bbmax, r.o, r.d);
+						}
+						r.max_distance = rw.max_distance;
+						r.index = idx;
+					} else {
+						uint32_t x, y;
+						valid = unit_pixel(pw, (uint32_t)(idx >> 5), (uint32_t)(idx & 31ull), x, y, out);
+						r.o = make_f3(0.0f, 0.0f, 2.0f);
+						r.d = primary_dir(pw.cam, x, y);
+						r.max_distance = 100000.0f;
+						r.index = out;
+					}
+					if (valid) {
+						r.best.dist = __int_as_float(0x7f800000); r.best.tri = 0xffffffffu; r.best.s = r.best.t = 0.f;
+						const bool plain = r.d.x != 0.0f && r.d.y != 0.0f && r.d.z != 0.0f;
+						if (ordered_ok && plain) {
+							r.id = make_f3(rn_div(1.0f, r.d.x), rn_div(1.0f, r.d.y), rn_div(1.0f, r.d.z));
+							r.inv_len = rsqrtf(fmaxf(r.d.x * r.d.x + r.d.y * r.d.y + r.d.z * r.d.z, 1e-30f));
+							r.abs_margin = 1e-5f * fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fmaxf(fabsf(r.o.z), sc.scene_scale)) * r.inv_len;
+							r.cull = __int_as_float(0x7f800000);
+							r.limit = r.max_distance;
+							r.cur = 0; r.pend = RTX_PT_NONE; r.sp = 0;
+						} else {       /* zero direction component / deep tree: the literal walk, right away */
+							if (COUNT) atomicAdd(&cnt->exact_rays, 1ull);
+							walk_reference<COUNT>(sc, r.o, r.d, r.max_distance, r.best, cnt);
+							r.cur = RTX_PT_DONE; r.pend = RTX_PT_NONE; r.sp = 0;
+						}
+						has_ray = true;
+					}
+				}
+			}
+		}
+		if (__ballot_sync(full, has_ray) == 0u) {
+			if (exhausted) break;
+			continue;
+		}
+		/* ---------------- descend ---------------- */
+		for (;;) {
+			const bool descending = has_ray && r.cur >= 0;
+			if (__popc(__ballot_sync(full, descending)) < RTX_PT_MIN_DESCEND && __ballot_sync(full, has_ray && r.pend != RTX_PT_NONE) != 0u) break;
+			if (__ballot_sync(full, descending) == 0u) break;
+			if (descending) {
+				const float4 *q = sc.pairs + 4 * (size_t)r.cur;
+				const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+				if (COUNT) visits += 2;
+				const Slab L = slab_interval<false, 4>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r.o, r.id);
+				const Slab R = slab_interval<false, 4>(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, r.o, r.id);
+				const bool hitL = L.tmin <= L.tmax && L.tmin < r.limit && L.tmax > 0.0f;
+				const bool hitR = R.tmin <= R.tmax && R.tmin < r.limit && R.tmax > 0.0f;
+				int next;
+				if (!(hitL || hitR)) {
+					next = pt_pop<SMEM_STACK>(r, s_stack, l_stack, stride);
+				} else {
+					const int refL = __float_as_int(q1.z), refR = __float_as_int(q3.z);
+					const bool r_first = hitR && (!hitL || R.tmin < L.tmin);
+					if (hitL && hitR) {
+						const uint2 e = make_uint2((uint32_t)(r_first ? refL : refR), __float_as_uint(r_first ? L.tmin : R.tmin));
+						if (SMEM_STACK > 0 && r.sp < SMEM_STACK) s_stack[r.sp * stride] = e; else l_stack[r.sp - SMEM_STACK] = e;
+						++r.sp;
+					}
+					next = r_first ? refR : refL;
+				}
+				/* a leaf is parked; with nothing parked yet the lane keeps descending from its stack */
+				if (next < 0 && next != RTX_PT_DONE && r.pend == RTX_PT_NONE) {
+					r.pend = next;
+					next = pt_pop<SMEM_STACK>(r, s_stack, l_stack, stride);
+				}
+				r.cur = next;
+			}
+		}
+		/* ---------------- leaves ---------------- */
+		if (has_ray && r.pend != RTX_PT_NONE) {
+			const uint32_t enc = ~(uint32_t)r.pend;
+			const uint32_t first = enc >> 3, count = (enc & 7u) + 1u;
+			for (uint32_t k = 0; k < count; ++k) {
+				const uint32_t tri = first + k;
+				const float4 *q = sc.tris + 4 * (size_t)tri;
+				TriHit h;
+				if (COUNT) ++tests;
+				if (!triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), r.o, r.d, r.cull, h)) continue;
+				if (!(h.dist < r.best.dist || (h.dist == r.best.dist && tri < r.best.tri))) continue;
+				if (sc.verify_leafbox) {
+					const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+					if (COUNT) ++lbtests;
+					if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), r.o, r.d, r.max_distance)) continue;
+				}
+				r.best.dist = h.dist; r.best.tri = tri; r.best.s = h.s; r.best.t = h.t;
+				r.cull = (h.dist * r.inv_len) * 1.0001f + r.abs_margin;
+				r.limit = fminf(r.max_distance, r.cull);
+			}
+			r.pend = RTX_PT_NONE;
+			if (r.cur < 0 && r.cur != RTX_PT_DONE) {        /* a second leaf was waiting: park it, move on */
+				r.pend = r.cur;
+				r.cur = pt_pop<SMEM_STACK>(r, s_stack, l_stack, stride);
+			}
+		}
+		/* ---------------- retire ---------------- */
+		if (has_ray && r.cur == RTX_PT_DONE && r.pend == RTX_PT_NONE) {
+			const uint32_t fid = r.best.tri != 0xffffffffu ? r.best.tri * 3u : 0xffffffffu;
+			if (SOURCE == 0) {
+				if (rw.face_id) rw.face_id[r.index] = fid;
+				if (rw.dist) rw.dist[r.index] = r.best.dist;
+				if (fid != 0xffffffffu) { ++hits; idsum += fid; }
+			} else {
+				float value = 0.0f;
+				if (r.best.tri != 0xffffffffu) value = shade_hit(sc.tnormals, r.best.tri, r.best.s, r.best.t, r.d, pw.cam.shading);
+				pw.image[r.index] = value;
+				if (RECORD) {
+					pw.face_id[r.index] = fid;
+					pw.dist[r.index] = r.best.dist;
+				}
+			}
+			has_ray = false;
+		}
+	}
+	if (SOURCE == 0 && rw.hit_count) {
+		for (int s = 16; s > 0; s >>= 1) {
+			hits += __shfl_xor_sync(full, hits, s);
+			idsum += __shfl_xor_sync(full, idsum, s);
+		}
+		if (lane == 0 && hits) { atomicAdd(rw.hit_count, hits); atomicAdd(rw.sum_face_id, idsum); }
+	}
+	if (COUNT) {
+		atomicAdd(&cnt->node_visits, visits);
+		atomicAdd(&cnt->tri_tests, tests);
+		atomicAdd(&cnt->leafbox_tests, lbtests);
+	}
+}
+
 /* ------------------------------ image ops -------------------------------- */
 
 /* RayTracer::resize (src/ray_tracer.cc:3-15): n x n box sum in (ssY, ssX)
