@@ -63,7 +63,7 @@ def build_scene(kind):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons of one GPU, sampled every 50 ms during the timed region."""
+    """SM clock + throttle reasons of one GPU, sampled every 2 ms during the timed region (frames take a few ms)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
         }
-        while not self.stop_flag:
+        while True:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -99,10 +99,14 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            if self.stop_flag:          # at least one sample is always taken
+                break
+            time.sleep(0.002)
 
     def result(self):
         self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1.0)
         if self.nv is None or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
