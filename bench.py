@@ -370,6 +370,30 @@ def main():
                   "calls": "rtx_upload + rtx_render(+gather) + rtx_download_u8 (device resize, ray_tracer.cc:3-15 order)",
                   "phase_ms": phases[1]}
 
+    # ---------------- extras (N = 1): same frame, other code paths, kernel time only ----------------
+    extras = None
+    if world == 1:
+        extras = {}
+
+        def kernel_ms(h, n=3):
+            best = 1e9
+            for _ in range(n):
+                h()
+                best = min(best, h.stats()["kernel_ms"])
+            return best
+
+        for name, tun, jit in (("reference_algorithm_on_gpu", {host.TUNE_KERNEL: host.KERNEL_EXHAUSTIVE}, 0),
+                               ("per_ray_traversal_no_frustum", {host.TUNE_FRUSTUM: 0}, 0),
+                               ("jittered_16spp_seed_0x5EED", {}, 0x5EED)):
+            with host.CudaHost(rt, device=local_rank, jitter_seed=jit) as hx:
+                for k, v in tun.items():
+                    hx.set_tunable(k, v)
+                hx.upload_scene(sc)
+                ms = kernel_ms(hx)
+                extras[name] = {"kernel_ms": ms, "Mrays/s": rays / ms / 1e3}
+        extras["reference_algorithm_on_gpu"]["what"] = ("k_render_exhaustive: the reference kernel's own algorithm (one thread per pixel, "
+                                                        "stackless pre-order walk, no culling) compiled for sm_100a")
+
     # ---------------- roofline + cpu baseline (rank 0, N = 1 only for the CPU leg) ----------------
     roofline = cpu = None
     if rank == 0:
@@ -423,7 +447,7 @@ def main():
                            " + 1 NCCL gather + de-interleave" if world > 1 else "", "byte" if args.gather == "u8" else "float"),
                        "l2": "flushed between timed iterations (256 MiB memset, untimed)"},
             "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(lt.item()),
-            "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "other_gather": other,
+            "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "other_gather": other, "extras": extras,
             "step_ms": [float(x) for x in step_ms],
         }))
     if world > 1:

@@ -110,6 +110,7 @@ typedef struct rtx_stats {
 #define RTX_TUNE_RAYS_PER_THREAD 8 /* primary rays per lane in the traversal kernel: 1, 2 (2x1 pixels), 4 (2x2 pixels), or 0 = the refill kernel */
 #define RTX_TUNE_FRUSTUM       9  /* frustum front end for 16x8-pixel packets: 0 off, 1 on, -1 auto */
 #define RTX_TUNE_LIST_RAYS_PER_THREAD 10 /* rays per lane in the candidate-list kernel: 1, 2 or 4 */
+#define RTX_TUNE_RAY_TABLES    12  /* 1 (default): per-column/row tables of the pixel terms of the primary ray direction */
 #define RTX_TUNE_INCOHERENT_KERNEL 11 /* arbitrary rays: 1 persistent refill + parked leaves (default), 0 plain while-while */
 
 #define RTX_KERNEL_PERSISTENT  0  /* persistent warps, ordered stack traversal, distance culling */

@@ -67,6 +67,7 @@ struct rtx_ctx {
 	int flatten_on_device = 1;
 	int rays_per_thread = 1;     /* traversal kernel: 1, 2 (2x1) or 4 (2x2) pixels per lane, 0 = refill kernel */
 	int list_rays_per_thread = 2; /* rays per lane in the candidate-list kernel: 1, 2 or 4 */
+	int ray_tables = 1;          /* per-column / per-row tables of the pixel terms of the primary ray */
 	int incoherent_kernel = 1;   /* 1: persistent refill + parked leaves for arbitrary rays, 0: plain while-while */
 	int frustum = -1;            /* frustum front end: 0 off, 1 on, -1 auto (rays per triangle >= 24) */
 	/* scene */
@@ -81,7 +82,7 @@ struct rtx_ctx {
 	uint32_t W = 0, H = 0, tiles_x = 0, tiles_y = 0, tiles_per_rank = 0, local_tiles = 0;
 	uint32_t rank = 0, world = 1;
 	float *ext_image = nullptr;  /* caller-owned output (rtx_bind_output) */
-	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums, d_lists, d_slists;
+	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums, d_lists, d_slists, d_raytab;
 	bool rendered = false, full_valid = false, u8_valid = false;
 	/* stats */
 	rtx_stats stats{};
@@ -506,7 +507,7 @@ void rtx_destroy(rtx_ctx *c)
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = { &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
-	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists, &c->d_slists };
+	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists, &c->d_slists, &c->d_raytab };
 	for (DevBuf *b : bufs) b->release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
@@ -535,6 +536,7 @@ int rtx_set_tunable(rtx_ctx *c, int which, int64_t v)
 		if (v != 1 && v != 2 && v != 4) return fail(c, RTX_ERR_ARG, "list rays per thread must be 1, 2 or 4");
 		c->list_rays_per_thread = (int)v; break;
 	case RTX_TUNE_INCOHERENT_KERNEL: c->incoherent_kernel = v != 0; break;
+	case RTX_TUNE_RAY_TABLES: c->ray_tables = v != 0; break;
 	case RTX_TUNE_FRUSTUM:
 		if (v < -1 || v > 1) return fail(c, RTX_ERR_ARG, "frustum must be -1, 0 or 1");
 		c->frustum = (int)v; break;
@@ -684,6 +686,17 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	w.cam.h_over_2a = (float)c->H / (2.0f * w.cam.a);               /* :288 */
 	w.cam.jitter_seed = c->opt.jitter_seed;
 	w.cam.shading = c->opt.enable_shading ? 1 : 0;
+	w.cam.ux = w.cam.vy = nullptr;
+	if (c->ray_tables && c->opt.jitter_seed == 0) {
+		CU(c, c->d_raytab.alloc(((size_t)c->W + c->H) * sizeof(float)));
+		float *ux = c->d_raytab.as<float>(), *vy = ux + c->W;
+		const uint32_t m = c->W > c->H ? c->W : c->H;
+		k_ray_tables<<<(m + 255) / 256, 256, 0, st>>>(w.cam, ux, vy);
+		CU(c, cudaGetLastError());
+		w.cam.ux = ux;
+		w.cam.vy = vy;
+	}
+	const uint32_t table_launch = w.cam.ux ? 1u : 0u;
 	w.tiles_x = c->tiles_x;
 	w.tiles_y = c->tiles_y;
 	w.rank = c->rank;
@@ -720,14 +733,14 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 		}
 		k_frustum_collect<<<(c->local_tiles + 7) / 8, 256, 0, st>>>(c->sc, w, two_level ? c->d_slists.as<uint32_t>() : nullptr, c->d_lists.as<uint32_t>());
 		CU(c, cudaGetLastError());
-		c->stats.kernel_launches = two_level ? 4 : 3;
+		c->stats.kernel_launches = (two_level ? 4 : 3) + table_launch;
 	}
 	CU(c, launch_render(c, w, st));
 	CU(c, cudaEventRecord(c->ev1, st));
 	c->ev_pending = true;
 	c->stats.rays = (uint64_t)c->local_tiles * RTX_TILE * RTX_TILE;
 	if (c->world == 1) c->stats.rays = (uint64_t)c->W * c->H;
-	if (!w.frustum) c->stats.kernel_launches = 1;
+	if (!w.frustum) c->stats.kernel_launches = 1 + table_launch;
 	c->stats.kernel_variant = (c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
 	c->rendered = true;
 	c->full_valid = false;

@@ -668,9 +668,8 @@ RTX_DEV void intersect_candidates(const SceneDev &sc, const uint32_t *__restrict
 			if (key < cull[r]) want |= 1u << r;
 		if (!__any_sync(0xffffffffu, want != 0)) break;       /* sorted: nobody wants the rest either */
 		if (want) {
-			const uint32_t first = enc >> 3, count = (enc & 7u) + 1u;
-			for (uint32_t j = 0; j < count; ++j) {
-				const uint32_t tri = first + j;
+			const uint32_t first = enc >> 3, last = first + (enc & 7u);
+			for (uint32_t tri = first; tri <= last; ++tri) {
 				const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
 				uint32_t m = 0;
 #pragma unroll
@@ -1097,6 +1096,14 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 		atomicAdd(&cnt->tri_tests, tests);
 		atomicAdd(&cnt->leafbox_tests, lbtests);
 	}
+}
+
+/* ux[x] = (x + 0.5)/a - W/(2a), vy[y] = -((y + 0.5)/a - H/(2a)): intersect_kernel.cl:287-288, once per column / row */
+__global__ void k_ray_tables(Camera cam, float *__restrict__ ux, float *__restrict__ vy)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < cam.W) ux[i] = rn_sub(rn_div(rn_add((float)i, 0.5f), cam.a), cam.w_over_2a);
+	if (i < cam.H) vy[i] = -rn_sub(rn_div(rn_add((float)i, 0.5f), cam.a), cam.h_over_2a);
 }
 
 /* ------------------------------ image ops -------------------------------- */

@@ -26,7 +26,7 @@ NO_HIT = 0xFFFFFFFF
 
 OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NOMEM = range(7)
 
-TUNE_KERNEL, TUNE_LEAF_SIZE, TUNE_RECORD_HITS, TUNE_COUNTERS, TUNE_TOP_SMEM, TUNE_BLOCKS_PER_SM, TUNE_FLATTEN_ON_DEVICE, TUNE_RAYS_PER_THREAD, TUNE_FRUSTUM, TUNE_LIST_RAYS_PER_THREAD, TUNE_INCOHERENT_KERNEL = range(1, 12)
+TUNE_KERNEL, TUNE_LEAF_SIZE, TUNE_RECORD_HITS, TUNE_COUNTERS, TUNE_TOP_SMEM, TUNE_BLOCKS_PER_SM, TUNE_FLATTEN_ON_DEVICE, TUNE_RAYS_PER_THREAD, TUNE_FRUSTUM, TUNE_LIST_RAYS_PER_THREAD, TUNE_INCOHERENT_KERNEL, TUNE_RAY_TABLES = range(1, 13)
 KERNEL_PERSISTENT, KERNEL_EXHAUSTIVE = 0, 1
 
 # every symbol include/rtx_b200.h declares (tests check the library exports them all)

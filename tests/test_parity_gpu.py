@@ -105,9 +105,28 @@ def test_frustum_front_end_forced(po, bunny_scene, soup_scene, list_rpt, leaf):
             h()
             check_against_oracle(host, po, sc, rt, h)
             st = h.stats()
-            assert st["kernel_launches"] >= 3
+            assert st["kernel_launches"] >= 4
             assert (st["packet_overflows"] > 0) == expect_overflow
             assert st["leafbox_tests"] > 0
+
+
+@pytest.mark.parametrize("rpt", [0, 1, 2, 4])
+@pytest.mark.parametrize("tables", [0, 1])
+def test_every_traversal_kernel(po, soup_scene, sibenik_scene, rpt, tables):
+    """The per-ray traversal kernels with the frustum front end off: refill kernel (0), one ray per lane (1),
+    thread-level packets of 2 and 4 pixels; with and without the per-column/row ray tables."""
+    host = require_gpu()
+    for sc, (w, h_) in ((soup_scene, (201, 113)), (sibenik_scene, (320, 180))):
+        rt = host.RayTracer(host.Options(width=w, height=h_, nSuperSamples=4))
+        with host.CudaHost(rt) as h:
+            h.set_tunable(host.TUNE_FRUSTUM, 0)
+            h.set_tunable(host.TUNE_RAYS_PER_THREAD, rpt)
+            h.set_tunable(host.TUNE_RAY_TABLES, tables)
+            h.set_tunable(host.TUNE_RECORD_HITS, 1)
+            h.upload_scene(sc)
+            h()
+            check_against_oracle(host, po, sc, rt, h)
+            assert h.stats()["kernel_launches"] == 1 + tables
 
 
 def test_frustum_auto_rule(po, soup_scene, bunny_scene):
@@ -118,7 +137,7 @@ def test_frustum_auto_rule(po, soup_scene, bunny_scene):
         with host.CudaHost(rt) as h:
             h.upload_scene(sc)
             h()
-            assert (h.stats()["kernel_launches"] > 1) == expect
+            assert (h.stats()["kernel_launches"] > 2) == expect
 
 
 def test_full_size_properties(po, sibenik_scene):
