@@ -76,6 +76,7 @@ struct rtx_ctx {
 	DevBuf d_pairs, d_tris, d_leafbox, d_tnormals, d_ref_nodes, d_ref_aabbs;
 	DevBuf t_faces, t_verts, t_vnormals, t_scan;   /* upload staging, kept between uploads */
 	std::vector<uint32_t> h_scan;
+	std::vector<size_t> h_ends;
 	f3 bbmin{}, bbmax{};
 	uint32_t tree_depth = 0;
 	/* image */
@@ -559,16 +560,9 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	if (naabbvec != 2 * nnodes) return fail(c, RTX_ERR_ARG, "aabbs must hold 2 vectors per node");
 	if (nverts != nnormals || nverts == 0) return fail(c, RTX_ERR_ARG, "one normal per vertex required");
 	if (ntris >= (1u << 28)) return fail(c, RTX_ERR_ARG, "too many triangles (limit 2^28)");
-	std::string why;
-	if (!validate_tree(nodes, nnodes, ntris, why)) return fail(c, RTX_ERR_ARG, "malformed BVH: " + why);
-	for (size_t i = 0; i < nfaceidx; ++i)
-		if (faces[i] >= nverts) return fail(c, RTX_ERR_ARG, "face index out of range");
 	CU(c, cudaSetDevice(c->device));
 	c->uploaded = false;
 	cudaStream_t st = c->stream;
-	const bool device_flatten = c->flatten_on_device && c->top_smem == 0;
-	size_t num_pairs = 0;
-	uint32_t depth = 0, top_pairs = 0;
 #define CUU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(c, e_, #call); } while (0)
 	CUU(c->t_faces.alloc(nfaceidx * 4));
 	CUU(c->t_verts.alloc(nverts * 16));
@@ -583,21 +577,34 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	CUU(cudaMemcpyAsync(c->t_vnormals.p, vnormals16, nverts * 16, cudaMemcpyHostToDevice, st));
 	CUU(cudaMemcpyAsync(c->d_ref_nodes.p, nodes, nnodes * 4, cudaMemcpyHostToDevice, st));
 	CUU(cudaMemcpyAsync(c->d_ref_aabbs.p, aabbs16, nnodes * 32, cudaMemcpyHostToDevice, st));
+	/* the copies above are in flight while the host validates and scans */
+	const bool device_flatten = c->flatten_on_device && c->top_smem == 0;
+	std::string why;
+	size_t num_pairs = 0;
+	uint32_t depth = 0, top_pairs = 0;
 	if (device_flatten) {
-		/* one host pass: the two prefix counts k_flatten_nodes needs, and the depth of the flattened tree */
+		/* ONE host pass over the nodes: the invariants of SURVEY 3.3 (validate_tree), the two prefix counts
+		 * k_flatten_nodes needs, and the depth of the flattened tree. */
+		if (nnodes == 0 || nodes[0] != nnodes || (nnodes & 1) == 0 || leaves_of((uint32_t)nnodes) != ntris)
+			return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: node count must be 2*triangles-1 and nodes[0] must equal it");
 		std::vector<uint32_t> &scan = c->h_scan;
 		scan.resize(2 * nnodes);
 		uint32_t *first_leaf = scan.data(), *pair_idx = scan.data() + nnodes;
-		std::vector<size_t> ends;          /* pre-order ends of the open internal nodes */
+		std::vector<size_t> &ends = c->h_ends;          /* pre-order ends of the open internal nodes */
+		ends.clear();
 		uint32_t nl = 0, np = 0;
 		const uint32_t K = (uint32_t)c->leaf_size;
 		for (size_t i = 0; i < nnodes; ++i) {
 			while (!ends.empty() && ends.back() == i) ends.pop_back();
 			first_leaf[i] = nl;
 			pair_idx[i] = np;
-			const uint32_t size = nodes[i];
+			const size_t size = nodes[i];
 			if (size == 1) { ++nl; continue; }
-			if (leaves_of(size) > K || i == 0) {
+			if ((size & 1) == 0 || i + size > nnodes) return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: subtree size out of range at node " + std::to_string(i));
+			const size_t l = nodes[i + 1];
+			if ((l & 1) == 0 || l + 2 > size || nodes[i + 1 + l] != size - 1 - l)
+				return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: children do not tile node " + std::to_string(i));
+			if (leaves_of((uint32_t)size) > K || i == 0) {
 				++np;
 				ends.push_back(i + size);
 				if (ends.size() > depth) depth = (uint32_t)ends.size();
@@ -605,6 +612,17 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 		}
 		if (nnodes == 1) { np = 1; depth = 1; }
 		num_pairs = np;
+	} else if (!validate_tree(nodes, nnodes, ntris, why)) {
+		return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: " + why);
+	}
+	{
+		uint32_t bad = 0;                          /* branch-free range check of the vertex indices */
+		for (size_t i = 0; i < nfaceidx; ++i) bad |= (uint32_t)(faces[i] >= nverts);
+		if (bad) return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "face index out of range");
+	}
+	if (device_flatten) {
+		const uint32_t K = (uint32_t)c->leaf_size;
+		std::vector<uint32_t> &scan = c->h_scan;
 		CUU(c->t_scan.alloc(2 * nnodes * 4));
 		CUU(c->d_pairs.alloc(4 * num_pairs * 64));
 		CUU(cudaMemcpyAsync(c->t_scan.p, scan.data(), 2 * nnodes * 4, cudaMemcpyHostToDevice, st));

@@ -129,6 +129,20 @@ def test_every_traversal_kernel(po, soup_scene, sibenik_scene, rpt, tables):
             assert h.stats()["kernel_launches"] == 1 + tables
 
 
+@pytest.mark.parametrize("w,h_,ss,focal", [(160, 90, 9, 0.35), (97, 211, 4, 3.0), (256, 64, 16, 1.0), (64, 64, 1, 0.05)])
+def test_frustum_front_end_cameras(po, sibenik_scene, w, h_, ss, focal):
+    """Frustum front end forced, unusual cameras: wide and narrow fields of view, portrait images, sample grids that
+    do not divide the 32-pixel tile (n = 3), odd sizes (zero-component rays inside packets)."""
+    host = require_gpu()
+    rt = host.RayTracer(host.Options(width=w, height=h_, nSuperSamples=ss, focalLength=focal))
+    with host.CudaHost(rt) as h:
+        h.set_tunable(host.TUNE_FRUSTUM, 1)
+        h.set_tunable(host.TUNE_RECORD_HITS, 1)
+        h.upload_scene(sibenik_scene)
+        h()
+        check_against_oracle(host, po, sibenik_scene, rt, h)
+
+
 def test_frustum_auto_rule(po, soup_scene, bunny_scene):
     """Auto mode: on when the frame has >= 24 rays per triangle (soup: 2400), off otherwise (bunny C1: 20)."""
     host = require_gpu()
