@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -227,19 +228,39 @@ void flatten(const uint32_t *nodes, const float *aabbs16, size_t n, int leaf_siz
 
 /* ------------------------------ launches -------------------------------- */
 
-struct Variant { int block, min_blocks, smem_stack; };
+/* Resident CTAs per SM of a kernel, asked once per (kernel, device, shared-memory size): the query and the
+ * shared-memory opt-in cost host time on every launch otherwise. */
+struct OccEntry { const void *kernel; int device; size_t smem; int occ; };
+static OccEntry g_occ[128];
+static int g_nocc = 0;
+static std::mutex g_occ_mutex;     /* contexts on different host threads share the table */
+
+template <typename K>
+cudaError_t resident_blocks(K kernel, int block, size_t smem, int device, int *occ_out)
+{
+	const void *key = reinterpret_cast<const void *>(kernel);
+	std::lock_guard<std::mutex> lock(g_occ_mutex);
+	for (int i = 0; i < g_nocc; ++i)
+		if (g_occ[i].kernel == key && g_occ[i].device == device && g_occ[i].smem == smem) { *occ_out = g_occ[i].occ; return cudaSuccess; }
+	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	int occ = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem);
+	if (e != cudaSuccess) return e;
+	if (occ < 1) occ = 1;
+	if (g_nocc < 128) g_occ[g_nocc++] = OccEntry{ key, device, smem, occ };
+	*occ_out = occ;
+	return cudaSuccess;
+}
 
 template <int BLOCK, int MINB, int SST, bool TOP, bool COUNT, bool RECORD>
 cudaError_t launch_render_t(rtx_ctx *c, const Work &w, cudaStream_t st, int blocks_per_sm)
 {
 	auto k = k_render_persistent<BLOCK, MINB, SST, TOP, COUNT, RECORD>;
 	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2) + (TOP ? (size_t)c->sc.top_pairs * 64 : 0);
-	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return e;
 	int occ = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BLOCK, smem);
+	cudaError_t e = resident_blocks(k, BLOCK, smem, c->device, &occ);
 	if (e != cudaSuccess) return e;
-	if (occ < 1) occ = 1;
 	if (blocks_per_sm > 0 && blocks_per_sm < occ) occ = blocks_per_sm;
 	const unsigned grid = (unsigned)(c->sm_count * occ);
 	k<<<grid, BLOCK, smem, st>>>(c->sc, w, c->d_counters.as<Counters>());
@@ -252,12 +273,9 @@ cudaError_t launch_pt(rtx_ctx *c, const RayWork &rw, const Work &pw, cudaStream_
 	constexpr int BLOCK = 256, MINB = 3, SST = 8;
 	auto k = k_trace_persistent<BLOCK, MINB, SST, COUNT, RECORD, SOURCE>;
 	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2);
-	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return e;
 	int occ = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BLOCK, smem);
+	cudaError_t e = resident_blocks(k, BLOCK, smem, c->device, &occ);
 	if (e != cudaSuccess) return e;
-	if (occ < 1) occ = 1;
 	if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
 	k<<<(unsigned)(c->sm_count * occ), BLOCK, smem, st>>>(c->sc, rw, pw, c->d_counters.as<Counters>());
 	return cudaGetLastError();
@@ -268,12 +286,9 @@ cudaError_t launch_packet_t(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
 	auto k = k_render_packet<BLOCK, MINB, SST, COUNT, RECORD, RX, RY, MODE>;
 	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2) + (MODE == 1 ? (size_t)(BLOCK / 32) * (2 * RTX_CCAP) * 4 : 0);
-	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return e;
 	int occ = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BLOCK, smem);
+	cudaError_t e = resident_blocks(k, BLOCK, smem, c->device, &occ);
 	if (e != cudaSuccess) return e;
-	if (occ < 1) occ = 1;
 	if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
 	k<<<(unsigned)(c->sm_count * occ), BLOCK, smem, st>>>(c->sc, w, c->d_counters.as<Counters>());
 	return cudaGetLastError();
@@ -339,12 +354,9 @@ cudaError_t launch_rays_t(rtx_ctx *c, const RayWork &w, cudaStream_t st)
 	constexpr int BLOCK = 256, MINB = 3, SST = 8;
 	auto k = k_trace_rays<BLOCK, MINB, SST, TOP, COUNT>;
 	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2) + (TOP ? (size_t)c->sc.top_pairs * 64 : 0);
-	cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return e;
 	int occ = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BLOCK, smem);
+	cudaError_t e = resident_blocks(k, BLOCK, smem, c->device, &occ);
 	if (e != cudaSuccess) return e;
-	if (occ < 1) occ = 1;
 	if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
 	k<<<(unsigned)(c->sm_count * occ), BLOCK, smem, st>>>(c->sc, w, c->d_counters.as<Counters>());
 	return cudaGetLastError();
