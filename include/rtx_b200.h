@@ -41,7 +41,7 @@ extern "C" {
 #define RTX_ERR_ARG          1  /* null pointer, inconsistent sizes, malformed BVH arrays */
 #define RTX_ERR_NO_DEVICE    2  /* "No device found" (opencl_host.cc:30-31) */
 #define RTX_ERR_CUDA         3  /* a CUDA runtime call failed; see rtx_last_error */
-#define RTX_ERR_UNSUPPORTED  4  /* option outside this path (ambient occlusion) */
+#define RTX_ERR_UNSUPPORTED  4  /* combination this library does not offer (see the call) */
 #define RTX_ERR_STATE        5  /* call order: render before upload, ... */
 #define RTX_ERR_NOMEM        6
 
@@ -58,11 +58,11 @@ typedef struct rtx_options {
 	                                   compiler_options.h:13-19 is applied inside rtx_create */
 	uint32_t n_super_samples;
 	int32_t  enable_shading;        /* SHADING_ENABLE */
-	int32_t  enable_ao;             /* must be 0: AO rays are outside this path (render -a 0) */
-	float    ao_max_distance;
-	uint32_t ao_num_samples;
-	int32_t  ao_method;
-	int32_t  ao_alpha_min, ao_alpha_max;
+	int32_t  enable_ao;             /* AO_ENABLE: ambient-occlusion rays (intersect_kernel.cl:214-277, 305-307) */
+	float    ao_max_distance;       /* AO_MAX_DISTANCE; same 6-digit round trip as focal_length */
+	uint32_t ao_num_samples;        /* AO_NUM_SAMPLES: rings (uniform) or random rays; 0 disables AO like the kernel's #if */
+	int32_t  ao_method;             /* AO_METHOD: 0 uniform rings, 1 random hemisphere (ray_tracer.h:10-13) */
+	int32_t  ao_alpha_min, ao_alpha_max; /* degrees (uniform method) */
 	int32_t  bvh_method;            /* informational */
 	uint32_t total_width, total_height; /* width/height * (unsigned)sqrt(n_super_samples); 0 = derive */
 	/* ---- extensions; all-zero reproduces the reference ---- */

@@ -85,6 +85,10 @@ struct rtx_ctx {
 	uint32_t rank = 0, world = 1;
 	float *ext_image = nullptr;  /* caller-owned output (rtx_bind_output) */
 	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums, d_lists, d_slists, d_raytab;
+	DevBuf d_hit_st, d_ao_ring;  /* ambient occlusion: (s, t) of the primary hits; sample table of the uniform method */
+	bool ao = false;
+	float ao_max_distance = 0.f; /* after the compiler_options.h round trip */
+	uint32_t ao_ring_cap = 0;
 	bool rendered = false, full_valid = false, u8_valid = false;
 	/* stats */
 	rtx_stats stats{};
@@ -320,7 +324,7 @@ cudaError_t launch_render_v(rtx_ctx *c, const Work &w, cudaStream_t st)
 
 cudaError_t launch_render(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
-	const bool top = c->top_smem > 0 && c->sc.top_pairs > 0, cnt = c->counters != 0, rec = c->record_hits != 0;
+	const bool top = c->top_smem > 0 && c->sc.top_pairs > 0, cnt = c->counters != 0, rec = w.face_id != nullptr;
 	if (c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok) {
 		const unsigned warps_per_block = 8, grid = (w.num_units + warps_per_block - 1) / warps_per_block;
 		if (grid == 0) return cudaSuccess;
@@ -468,8 +472,20 @@ int rtx_create(rtx_ctx **out, const rtx_options *options)
 {
 	if (!out || !options) return fail(nullptr, RTX_ERR_ARG, "null argument");
 	*out = nullptr;
-	if (options->enable_ao && options->ao_num_samples > 0)
-		return fail(nullptr, RTX_ERR_UNSUPPORTED, "ambient occlusion is outside this path: run with -a 0");
+	const bool ao = options->enable_ao && options->ao_num_samples > 0;       /* intersect_kernel.cl:305 */
+	uint64_t ring_cap = 0;
+	if (ao) {
+		if (options->ao_method != 0 && options->ao_method != 1)
+			return fail(nullptr, RTX_ERR_ARG, "ambient occlusion method must be 0 (uniform) or 1 (random)");
+		if (options->ao_method == 0) {
+			/* rays per ring <= 2 pi / step + 1 with step = alpha_max / samples (intersect_kernel.cl:238-242) */
+			if (options->ao_alpha_max <= 0 || options->ao_alpha_max > 360)
+				return fail(nullptr, RTX_ERR_ARG, "uniform ambient occlusion needs 0 < alpha_max <= 360 degrees");
+			const double step = (double)options->ao_alpha_max * 3.14159265358979323846 / 180.0 / (double)options->ao_num_samples;
+			ring_cap = (uint64_t)options->ao_num_samples * ((uint64_t)(6.2831853071795865 / step) + 2);
+			if (ring_cap > (1u << 22)) return fail(nullptr, RTX_ERR_ARG, "too many ambient occlusion rings");
+		}
+	}
 	if (options->width == 0 || options->height == 0) return fail(nullptr, RTX_ERR_ARG, "empty image");
 	int ndev = 0;
 	const int rc = rtx_device_count(&ndev);
@@ -480,6 +496,9 @@ int rtx_create(rtx_ctx **out, const rtx_options *options)
 	c->opt = *options;
 	c->device = options->device;
 	c->focal = focal_roundtrip(options->focal_length);
+	c->ao = ao;
+	c->ao_max_distance = focal_roundtrip(options->ao_max_distance);              /* same -D round trip (opencl_host.cc:49) */
+	c->ao_ring_cap = (uint32_t)ring_cap;
 	const unsigned n = (unsigned)std::sqrt((double)options->n_super_samples);   /* ray_tracer.h:33-34 */
 	c->W = options->total_width ? options->total_width : options->width * n;
 	c->H = options->total_height ? options->total_height : options->height * n;
@@ -520,7 +539,8 @@ void rtx_destroy(rtx_ctx *c)
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = { &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
-	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists, &c->d_slists, &c->d_raytab };
+	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists, &c->d_slists, &c->d_raytab,
+	                   &c->d_hit_st, &c->d_ao_ring };
 	for (DevBuf *b : bufs) b->release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
@@ -704,10 +724,12 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	if (!c->uploaded) return fail(c, RTX_ERR_STATE, "render before upload");
 	CU(c, cudaSetDevice(c->device));
 	const size_t out_n = c->world > 1 ? (size_t)c->tiles_per_rank * RTX_TILE * RTX_TILE : (size_t)c->W * c->H;
-	if (c->record_hits) {
+	const bool rec = c->record_hits || c->ao;      /* the occlusion pass starts from the recorded hits */
+	if (rec) {
 		CU(c, c->d_face_id.alloc(out_n * 4));
 		CU(c, c->d_dist.alloc(out_n * 4));
 	}
+	if (c->ao) CU(c, c->d_hit_st.alloc(out_n * sizeof(float2)));
 	Work w{};
 	w.cam.W = c->W;
 	w.cam.H = c->H;
@@ -735,8 +757,9 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	w.num_units = c->local_tiles * 32u;
 	w.counter = c->d_counter.as<unsigned int>();
 	w.image = c->ext_image ? c->ext_image : c->d_image.as<float>();
-	w.face_id = c->record_hits ? c->d_face_id.as<uint32_t>() : nullptr;
-	w.dist = c->record_hits ? c->d_dist.as<float>() : nullptr;
+	w.face_id = rec ? c->d_face_id.as<uint32_t>() : nullptr;
+	w.dist = rec ? c->d_dist.as<float>() : nullptr;
+	w.hit_st = c->ao ? c->d_hit_st.as<float2>() : nullptr;
 	w.ordered_ok = c->tree_depth <= RTX_STACK_MAX ? 1 : 0;
 	/* frustum front end pays off when packets see few triangles: many rays per triangle */
 	const double rays_per_tri = (double)c->W * c->H / (double)c->sc.num_tris;
@@ -766,11 +789,33 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 		c->stats.kernel_launches = (two_level ? 4 : 3) + table_launch;
 	}
 	CU(c, launch_render(c, w, st));
+	uint32_t ao_launches = 0;
+	if (c->ao && w.num_units > 0) {
+		/* second pass over the hit pixels (intersect_kernel.cl:305-307) */
+		AoParams ao{};
+		ao.method = c->opt.ao_method;
+		ao.samples = c->opt.ao_num_samples;
+		ao.max_distance = c->ao_max_distance;
+		ao.alpha_min = c->opt.ao_alpha_min;
+		ao.alpha_max = c->opt.ao_alpha_max;
+		if (ao.method == 0) {
+			CU(c, c->d_ao_ring.alloc(((size_t)c->ao_ring_cap + 1) * sizeof(float4)));
+			ao.ring = c->d_ao_ring.as<float4>();
+			ao.ring_cap = c->ao_ring_cap;
+			k_ao_ring_table<<<1, 32, 0, st>>>(ao, c->d_ao_ring.as<float4>());
+			CU(c, cudaGetLastError());
+			++ao_launches;
+		}
+		k_ambient_occlusion<<<(w.num_units + 3) / 4, 128, 0, st>>>(c->sc, w, ao);
+		CU(c, cudaGetLastError());
+		++ao_launches;
+	}
 	CU(c, cudaEventRecord(c->ev1, st));
 	c->ev_pending = true;
 	c->stats.rays = (uint64_t)c->local_tiles * RTX_TILE * RTX_TILE;
 	if (c->world == 1) c->stats.rays = (uint64_t)c->W * c->H;
 	if (!w.frustum) c->stats.kernel_launches = 1 + table_launch;
+	c->stats.kernel_launches += ao_launches;
 	c->stats.kernel_variant = (c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
 	c->rendered = true;
 	c->full_valid = false;

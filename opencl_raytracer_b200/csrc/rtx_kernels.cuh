@@ -264,6 +264,7 @@ struct Work {
 	float *image;                /* world == 1: row-major W x H; else compact [local_tile][32][32] */
 	uint32_t *face_id;           /* optional (record mode), same indexing as image */
 	float *dist;
+	float2 *hit_st;              /* optional (ambient occlusion): parametric coordinates of the hit */
 	int ordered_ok;
 	int frustum;                 /* use the frustum front end for packets */
 	const uint32_t *lists;       /* per-tile candidate lists written by k_frustum_collect */
@@ -296,6 +297,7 @@ RTX_DEV void trace_pixel(const SceneDev &sc, const Work &w, const float4 *s_top,
 	if (RECORD) {
 		w.face_id[out] = best.tri != 0xffffffffu ? best.tri * 3u : 0xffffffffu;
 		w.dist[out] = best.dist;
+		if (w.hit_st) w.hit_st[out] = make_float2(best.s, best.t);
 	}
 }
 
@@ -796,6 +798,7 @@ k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 			if (RECORD) {
 				w.face_id[out[r]] = best[r].tri != 0xffffffffu ? best[r].tri * 3u : 0xffffffffu;
 				w.dist[out[r]] = best[r].dist;
+				if (w.hit_st) w.hit_st[out[r]] = make_float2(best[r].s, best[r].t);
 			}
 		}
 		__syncwarp();
@@ -824,6 +827,7 @@ k_render_exhaustive(const SceneDev sc, const Work w, Counters *cnt)
 	if (RECORD) {
 		w.face_id[out] = best.tri != 0xffffffffu ? best.tri * 3u : 0xffffffffu;
 		w.dist[out] = best.dist;
+		if (w.hit_st) w.hit_st[out] = make_float2(best.s, best.t);
 	}
 }
 
@@ -1079,6 +1083,7 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 				if (RECORD) {
 					pw.face_id[r.index] = fid;
 					pw.dist[r.index] = r.best.dist;
+					if (pw.hit_st) pw.hit_st[r.index] = make_float2(r.best.s, r.best.t);
 				}
 			}
 			has_ray = false;
@@ -1096,6 +1101,229 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 		atomicAdd(&cnt->tri_tests, tests);
 		atomicAdd(&cnt->leafbox_tests, lbtests);
 	}
+}
+
+/* --------------------------------------------------------------------------
+ * Ambient occlusion (intersect_kernel.cl:128-183, 214-277, 305-307): a second pass over the hit pixels.
+ * The primary pass records (triangle, s, t); this kernel recomputes the hit point and the smooth normal with
+ * the operations of :71-85 and :118-127 (so they are the values the reference held in registers), shoots
+ * the occlusion rays and multiplies the pixel.  An occlusion ray only asks "does ANY candidate triangle
+ * hit?" (:251,:264,:270 use the bool); candidates are, as everywhere, the triangles whose leaf box passes
+ * the slab test with max_distance = AO_MAX_DISTANCE, so any traversal that finds one may stop.
+ * Transcendentals follow the oracle's definition: evaluate in double, round once to float.
+ * ------------------------------------------------------------------------ */
+struct AoParams {
+	int method;             /* 0 uniform rings, 1 random hemisphere */
+	uint32_t samples;
+	float max_distance;
+	int alpha_min, alpha_max;
+	const float4 *ring;     /* method 0: ring[0].x = bits(number of rays), ring[1..] = (xs, ys, zs, 0) per ray */
+	uint32_t ring_cap;
+};
+
+RTX_DEV float t_sin(float x) { return (float)sin((double)x); }
+RTX_DEV float t_cos(float x) { return (float)cos((double)x); }
+RTX_DEV float t_acos(float x) { return (float)acos((double)x); }
+RTX_DEV float t_cospi(float x) { return (float)cos((double)rn_mul(3.14159265358979323846f, x)); }
+RTX_DEV float t_sinpi(float x) { return (float)sin((double)rn_mul(3.14159265358979323846f, x)); }
+
+RTX_DEV f3 normalize3(f3 a)
+{
+	const float len = rn_sqrt(dot3(a, a));
+	return make_f3(rn_div(a.x, len), rn_div(a.y, len), rn_div(a.z, len));
+}
+RTX_DEV f3 perturb_smallest(f3 h)       /* :156-164, :226-234 */
+{
+	if (fabsf(h.x) <= fabsf(h.y) && fabsf(h.x) <= fabsf(h.z)) h.x = 1.0f;
+	else if (fabsf(h.y) <= fabsf(h.x) && fabsf(h.y) <= fabsf(h.z)) h.y = 1.0f;
+	else if (fabsf(h.z) <= fabsf(h.x) && fabsf(h.z) <= fabsf(h.y)) h.z = 1.0f;
+	return h;
+}
+/* basis_x * xs + basis_y * ys + basis_z * zs, per component ((x + y) + z) */
+RTX_DEV f3 combine3(f3 bx, float xs, f3 by, float ys, f3 bz, float zs)
+{
+	return make_f3(rn_add(rn_add(rn_mul(bx.x, xs), rn_mul(by.x, ys)), rn_mul(bz.x, zs)),
+	               rn_add(rn_add(rn_mul(bx.y, xs), rn_mul(by.y, ys)), rn_mul(bz.y, zs)),
+	               rn_add(rn_add(rn_mul(bx.z, xs), rn_mul(by.z, ys)), rn_mul(bz.z, zs)));
+}
+RTX_DEV uint32_t ao_random_int(uint32_t (&v)[4])      /* :128-135 */
+{
+	const uint32_t t = v[0] ^ (v[0] << 11u);
+	v[0] = v[1]; v[1] = v[2]; v[2] = v[3];
+	return v[3] = v[3] ^ (v[3] >> 19u) ^ (t ^ (t >> 8u));
+}
+RTX_DEV float ao_random_float(uint32_t (&v)[4]) { return rn_mul(2.32830643653869629E-10f, (float)ao_random_int(v)); }
+
+/* the literal walk, asking only for "any hit" */
+__device__ __noinline__ bool walk_reference_any(const SceneDev &sc, f3 o, f3 d, float max_distance)
+{
+	const uint32_t n = __ldg(sc.ref_nodes);
+	uint32_t tri = 0;
+	for (uint32_t i = 0; i < n;) {
+		const uint32_t node_count = __ldg(sc.ref_nodes + i);
+		const float4 lo = __ldg(sc.ref_aabbs + 2 * (size_t)i), hi = __ldg(sc.ref_aabbs + 2 * (size_t)i + 1);
+		if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), o, d, max_distance)) {
+			tri += (node_count + 1) >> 1;
+			i += node_count;
+		} else {
+			if (node_count == 1) {
+				const float4 *q = sc.tris + 4 * (size_t)tri;
+				TriHit h;
+				if (triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, __int_as_float(0x7f800000), h)) return true;
+				++tri;
+			}
+			++i;
+		}
+	}
+	return false;
+}
+
+RTX_DEV bool any_hit(const SceneDev &sc, bool ordered_ok, f3 o, f3 d, float max_distance)
+{
+	const bool plain = d.x != 0.0f && d.y != 0.0f && d.z != 0.0f && d.x == d.x && d.y == d.y && d.z == d.z;
+	if (!(ordered_ok && plain)) return walk_reference_any(sc, o, d, max_distance);
+	const f3 id = make_f3(rn_div(1.0f, d.x), rn_div(1.0f, d.y), rn_div(1.0f, d.z));
+	int stack[RTX_STACK_MAX];
+	int sp = 0, cur = 0;
+	for (;;) {
+		while (cur >= 0) {
+			const float4 *q = sc.pairs + 4 * (size_t)cur;
+			const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+			const Slab L = slab_interval<false, 4>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, id);
+			const Slab R = slab_interval<false, 4>(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, o, id);
+			const bool hitL = L.tmin <= L.tmax && L.tmin < max_distance && L.tmax > 0.0f;
+			const bool hitR = R.tmin <= R.tmax && R.tmin < max_distance && R.tmax > 0.0f;
+			if (!(hitL || hitR)) goto pop;
+			const int refL = __float_as_int(q1.z), refR = __float_as_int(q3.z);
+			const bool r_first = hitR && (!hitL || R.tmin < L.tmin);
+			if (hitL && hitR) stack[sp++] = r_first ? refL : refR;
+			cur = r_first ? refR : refL;
+		}
+		{
+			const uint32_t enc = ~(uint32_t)cur;
+			const uint32_t first = enc >> 3, last = first + (enc & 7u);
+			for (uint32_t tri = first; tri <= last; ++tri) {
+				const float4 *q = sc.tris + 4 * (size_t)tri;
+				TriHit h;
+				if (!triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, __int_as_float(0x7f800000), h)) continue;
+				if (sc.verify_leafbox) {
+					const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+					if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), o, d, max_distance)) continue;
+				}
+				return true;
+			}
+		}
+pop:
+		if (sp == 0) return false;
+		cur = stack[--sp];
+	}
+}
+
+/* The sample directions of the uniform method in the local basis (:236-246), once per frame: they depend on
+ * (ring, ray) only.  One thread; the sequence is a few dozen to a few hundred entries. */
+__global__ void k_ao_ring_table(AoParams ao, float4 *__restrict__ ring)
+{
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	const double PI = 3.14159265358979323846, PI_2 = 1.57079632679489661923;
+	const uint32_t circle_count = ao.samples;
+	const float degrees = (float)(PI / 180);                                            /* :221 */
+	const float alpha_min = rn_mul((float)ao.alpha_min, degrees), alpha_max = rn_mul((float)ao.alpha_max, degrees);
+	uint32_t n = 0;
+	for (uint32_t cc = 0; cc < circle_count; ++cc) {
+		const float step = rn_div(alpha_max, (float)circle_count);                      /* :238 */
+		const float angle = rn_add(rn_mul(step, (float)cc), alpha_min);                 /* :239 */
+		const uint32_t ray_count = (uint32_t)__ddiv_rn(__dmul_rn(__dmul_rn(2.0, PI), (double)t_cos(angle)), (double)step); /* :240 */
+		const float theta = (float)__dsub_rn(PI_2, (double)angle);                      /* :241 */
+		for (uint32_t cr = 0; cr <= ray_count; ++cr) {                                  /* :242 (<=) */
+			const float phi = (float)__ddiv_rn(__dmul_rn(__dmul_rn(2.0, PI), (double)cr), (double)ray_count); /* :243 */
+			const float xs = rn_mul(t_sin(theta), t_cospi(phi));
+			const float ys = t_cos(theta);
+			const float zs = rn_mul(t_sin(theta), t_sinpi(phi));
+			if (n < ao.ring_cap) ring[1 + n] = make_float4(xs, ys, zs, 0.0f);
+			++n;
+		}
+	}
+	ring[0] = make_float4(__uint_as_float(n < ao.ring_cap ? n : ao.ring_cap), 0.f, 0.f, 0.f);
+}
+
+/* :214-277 */
+RTX_DEV float ambient_occlusion(const SceneDev &sc, bool ordered_ok, f3 point, f3 normal, uint32_t index, const AoParams &ao)
+{
+	const float k = rn_div(1.0f, 100000.0f);
+	const f3 p = make_f3(rn_add(point.x, rn_mul(normal.x, k)), rn_add(point.y, rn_mul(normal.y, k)), rn_add(point.z, rn_mul(normal.z, k))); /* :215 */
+	uint32_t hits = 0;
+	if (ao.method == 0) {                                                    /* :218-256 */
+		const f3 basis_y = normal;
+		const f3 h = perturb_smallest(basis_y);
+		const f3 basis_x = normalize3(cross3(h, basis_y));
+		const f3 basis_z = normalize3(cross3(basis_x, basis_y));
+		/* (xs, ys, zs) of :244-246 depend on the ring and the ray only, not on the pixel: k_ao_ring_table */
+		const uint32_t n = __float_as_uint(__ldg(ao.ring).x);
+		for (uint32_t i = 0; i < n; ++i) {
+			const float4 s = __ldg(ao.ring + 1 + i);
+			const f3 dir = combine3(basis_x, s.x, basis_y, s.y, basis_z, s.z);   /* :248 */
+			if (any_hit(sc, ordered_ok, p, dir, ao.max_distance)) ++hits;
+		}
+		return rn_sub(1.0f, rn_div((float)hits, (float)n));                  /* :256 */
+	}
+	/* random hemisphere :257-275, sampler :153-183 */
+	const f3 basis_y = normalize3(normal);
+	const f3 h = perturb_smallest(basis_y);
+	const f3 basis_x = normalize3(cross3(h, basis_y));
+	const f3 basis_z = normalize3(cross3(basis_x, basis_y));
+	uint32_t rng[4];
+	const uint32_t seed = 536870923u * index;
+	rng[0] = (123456789u ^ seed) * 88675123u;
+	rng[1] = (362436069u ^ seed) * 123456789u;
+	rng[2] = (521288629u ^ seed) * 362436069u;
+	rng[3] = (88675123u ^ seed) * 521288629u;
+	ao_random_int(rng);
+	const uint32_t n = ao.samples + 1u;
+	if (any_hit(sc, ordered_ok, p, normal, ao.max_distance)) ++hits;
+	for (uint32_t i = 0; i < n; ++i) {
+		const float xi1 = ao_random_float(rng);
+		const float xi2 = ao_random_float(rng);
+		const float theta = t_acos(rn_sqrt(rn_sub(1.0f, xi1)));
+		const float phi = (float)__dmul_rn(2.0, (double)xi2);
+		const float xs = rn_mul(t_sin(theta), t_cospi(phi));
+		const float ys = t_cos(theta);
+		const float zs = rn_mul(t_sin(theta), t_sinpi(phi));
+		const f3 dir = normalize3(combine3(basis_x, xs, basis_y, ys, basis_z, zs));
+		if (any_hit(sc, ordered_ok, p, dir, ao.max_distance)) ++hits;
+	}
+	return rn_sub(1.0f, rn_div((float)hits, (float)n));
+}
+
+/* One lane per pixel, 8x4-pixel blocks like the primary pass. */
+__global__ void __launch_bounds__(128)
+k_ambient_occlusion(const SceneDev sc, const Work w, const AoParams ao)
+{
+	const uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (unit >= w.num_units) return;
+	uint32_t x, y;
+	size_t out;
+	if (!unit_pixel(w, unit, threadIdx.x & 31u, x, y, out)) return;
+	const uint32_t fid = w.face_id[out];
+	if (fid == 0xffffffffu) return;
+	const uint32_t tri = fid / 3u;
+	const float2 st = w.hit_st[out];
+	const f3 o = make_f3(0.0f, 0.0f, 2.0f);
+	const f3 d = primary_dir(w.cam, x, y);
+	/* the hit point as triangle_test computed it (:71-85) */
+	const float4 *q = sc.tris + 4 * (size_t)tri;
+	const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+	const f3 a = make_f3(q0.x, q0.y, q0.z), nrm = make_f3(q0.w, q1.w, q2.w);
+	const f3 w0 = sub3(o, a);
+	const float r = rn_div(-dot3(nrm, w0), dot3(nrm, d));
+	const f3 point = make_f3(rn_add(o.x, rn_mul(r, d.x)), rn_add(o.y, rn_mul(r, d.y)), rn_add(o.z, rn_mul(r, d.z)));
+	/* the smooth normal (:118-127) */
+	const float4 n0 = __ldg(sc.tnormals + 3 * (size_t)tri), n1 = __ldg(sc.tnormals + 3 * (size_t)tri + 1), n2 = __ldg(sc.tnormals + 3 * (size_t)tri + 2);
+	const float b0 = rn_sub(rn_sub(1.0f, st.x), st.y), b1 = st.x, b2 = st.y;
+	const f3 normal = normalize3(make_f3(rn_add(rn_add(rn_mul(n0.x, b0), rn_mul(n1.x, b1)), rn_mul(n2.x, b2)),
+	                                     rn_add(rn_add(rn_mul(n0.y, b0), rn_mul(n1.y, b1)), rn_mul(n2.y, b2)),
+	                                     rn_add(rn_add(rn_mul(n0.z, b0), rn_mul(n1.z, b1)), rn_mul(n2.z, b2))));
+	const float occlusion = ambient_occlusion(sc, w.ordered_ok != 0, point, normal, y * w.cam.W + x, ao);
+	w.image[out] = rn_mul(w.image[out], occlusion);                         /* :306 */
 }
 
 /* ux[x] = (x + 0.5)/a - W/(2a), vy[y] = -((y + 0.5)/a - H/(2a)): intersect_kernel.cl:287-288, once per column / row */

@@ -51,6 +51,16 @@ class Counters(C.Structure):
         return d
 
 
+class Ao(C.Structure):
+    """Ambient-occlusion options (orc_ao): method 0 = uniform rings, 1 = random hemisphere."""
+    _fields_ = [("enable", C.c_int), ("method", C.c_int), ("samples", C.c_uint32), ("max_distance", C.c_float),
+                ("alpha_min", C.c_int), ("alpha_max", C.c_int)]
+
+    @classmethod
+    def make(cls, method=0, samples=3, max_distance=0.2, alpha_min=4, alpha_max=90):
+        return cls(1, method, samples, max_distance, alpha_min, alpha_max)
+
+
 def algorithmic_bytes_per_ray(V: float, T: float, h: float, extra: float = 0.0) -> float:
     """B = 32 V + 48 T + 48 h + 4 (+extra)."""
     return 32.0 * V + 48.0 * T + 48.0 * h + 4.0 + extra
@@ -98,6 +108,10 @@ def port():
         lib.orc_render.argtypes = [C.POINTER(_OrcScene), C.c_uint, C.c_uint, C.c_float, C.c_int, C.c_uint32,
                                    C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(Counters), C.c_int]
+        lib.orc_render_ao.restype = C.c_int
+        lib.orc_render_ao.argtypes = [C.POINTER(_OrcScene), C.c_uint, C.c_uint, C.c_float, C.c_int, C.c_uint32, C.POINTER(Ao),
+                                      C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.POINTER(Counters), C.c_int]
         lib.orc_trace_rays.restype = C.c_int
         lib.orc_trace_rays.argtypes = [C.POINTER(_OrcScene), C.c_void_p, C.c_void_p, C.c_size_t, C.c_float,
                                        C.c_void_p, C.c_void_p, C.POINTER(Counters), C.c_int]
@@ -136,6 +150,9 @@ def ref():
         lib.ref_render.restype = C.c_int
         lib.ref_render.argtypes = [C.POINTER(_OrcScene), C.c_uint, C.c_uint, C.c_float, C.c_int,
                                    C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_int]
+        lib.ref_render_ao.restype = C.c_int
+        lib.ref_render_ao.argtypes = [C.POINTER(_OrcScene), C.c_uint, C.c_uint, C.c_float, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                      C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_int]
         lib.ref_trace_rays.restype = C.c_int
         lib.ref_trace_rays.argtypes = [C.POINTER(_OrcScene), C.c_void_p, C.c_void_p, C.c_size_t, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_int]
@@ -160,7 +177,7 @@ def focal_roundtrip(f: float) -> float:
 
 
 def render(scene, width: int, height: int, focal: float = 1.0, shading: bool = True, jitter_seed: int = 0,
-           rows=None, want_ids: bool = True, want_counters: bool = False, nthreads: int = 0):
+           rows=None, want_ids: bool = True, want_counters: bool = False, nthreads: int = 0, ao: "Ao | None" = None):
     """intersect_kernel.cl:278-310 over width x height (super-sampled dims).
 
     rows = (begin, end, step) restricts the rows rendered.  Returns a
@@ -172,7 +189,8 @@ def render(scene, width: int, height: int, focal: float = 1.0, shading: bool = T
     fid = np.full((height, width), NO_HIT, np.uint32) if want_ids else None
     dist = np.full((height, width), np.inf, np.float32) if want_ids else None
     cnt = Counters() if want_counters else None
-    rc = port().orc_render(C.byref(s), width, height, C.c_float(focal), int(bool(shading)), jitter_seed,
+    rc = port().orc_render_ao(C.byref(s), width, height, C.c_float(focal), int(bool(shading)), jitter_seed,
+                           C.byref(ao) if ao is not None else None,
                            b, e, st, image.ctypes.data,
                            fid.ctypes.data if want_ids else None, dist.ctypes.data if want_ids else None,
                            C.byref(cnt) if cnt is not None else None, nthreads)
@@ -281,6 +299,19 @@ def ref_render(scene, width: int, height: int, focal: float = 1.0, shading: bool
                           image.ctypes.data, nthreads)
     if rc != 0:
         raise RuntimeError("ref_render failed")
+    del keep
+    return image
+
+
+def ref_render_ao(scene, width: int, height: int, ao: Ao, focal: float = 1.0, rows=None, nthreads: int = 0):
+    """The reference kernel text with AO_ENABLE (shading on); (method, samples) must be one of the compiled copies."""
+    s, keep = _keep(scene)
+    b, e, st = rows if rows is not None else (0, height, 1)
+    image = np.zeros((height, width), np.float32)
+    rc = ref().ref_render_ao(C.byref(s), width, height, C.c_float(focal), ao.method, ao.samples, C.c_float(ao.max_distance),
+                             ao.alpha_min, ao.alpha_max, b, e, st, image.ctypes.data, nthreads)
+    if rc != 0:
+        raise RuntimeError("ref_render_ao failed (%d)" % rc)
     del keep
     return image
 

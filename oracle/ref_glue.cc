@@ -37,13 +37,18 @@ static float g_focal;
 #define WIDTH g_width
 #define HEIGHT g_height
 #define FOCAL_LENGTH g_focal
-#define AO_METHOD 1
-#define AO_NUM_SAMPLES 0
-#define AO_MAX_DISTANCE .2f
-#define AO_ALPHA_MIN 4
-#define AO_ALPHA_MAX 90
+/* AO parameters that the kernel only uses inside expressions can be variables; AO_NUM_SAMPLES and AO_METHOD
+ * steer the preprocessor (intersect_kernel.cl:218,257,305), so every (method, samples) pair the tests use is
+ * its own compiled copy of the kernel text. */
+static float g_ao_max_distance = .2f;
+static int g_ao_alpha_min = 4, g_ao_alpha_max = 90;
+#define AO_MAX_DISTANCE g_ao_max_distance
+#define AO_ALPHA_MIN g_ao_alpha_min
+#define AO_ALPHA_MAX g_ao_alpha_max
 
 #define inline static inline
+#define AO_METHOD 1
+#define AO_NUM_SAMPLES 0
 namespace shaded {
 #define SHADING_ENABLE
 #include "kernel_as_cpp.inc"
@@ -52,7 +57,83 @@ namespace shaded {
 namespace flat {
 #include "kernel_as_cpp.inc"
 }
+#undef AO_METHOD
+#undef AO_NUM_SAMPLES
+#define AO_ENABLE
+#define SHADING_ENABLE
+#define AO_METHOD 0
+#define AO_NUM_SAMPLES 1
+namespace ao_m0_n1 {
+#include "kernel_as_cpp.inc"
+}
+#undef AO_METHOD
+#undef AO_NUM_SAMPLES
+#define AO_METHOD 0
+#define AO_NUM_SAMPLES 2
+namespace ao_m0_n2 {
+#include "kernel_as_cpp.inc"
+}
+#undef AO_METHOD
+#undef AO_NUM_SAMPLES
+#define AO_METHOD 0
+#define AO_NUM_SAMPLES 3
+namespace ao_m0_n3 {
+#include "kernel_as_cpp.inc"
+}
+#undef AO_METHOD
+#undef AO_NUM_SAMPLES
+#define AO_METHOD 0
+#define AO_NUM_SAMPLES 4
+namespace ao_m0_n4 {
+#include "kernel_as_cpp.inc"
+}
+#undef AO_METHOD
+#undef AO_NUM_SAMPLES
+#define AO_METHOD 1
+#define AO_NUM_SAMPLES 1
+namespace ao_m1_n1 {
+#include "kernel_as_cpp.inc"
+}
+#undef AO_METHOD
+#undef AO_NUM_SAMPLES
+#define AO_METHOD 1
+#define AO_NUM_SAMPLES 2
+namespace ao_m1_n2 {
+#include "kernel_as_cpp.inc"
+}
+#undef AO_METHOD
+#undef AO_NUM_SAMPLES
+#define AO_METHOD 1
+#define AO_NUM_SAMPLES 3
+namespace ao_m1_n3 {
+#include "kernel_as_cpp.inc"
+}
+#undef AO_METHOD
+#undef AO_NUM_SAMPLES
+#define AO_METHOD 1
+#define AO_NUM_SAMPLES 4
+namespace ao_m1_n4 {
+#include "kernel_as_cpp.inc"
+}
+#undef AO_METHOD
+#undef AO_NUM_SAMPLES
+#undef AO_ENABLE
+#undef SHADING_ENABLE
 #undef inline
+
+typedef void (*ref_kernel_fn)(const uint *, const uint *, const float4 *, const float4 *, const float4 *, float *);
+static ref_kernel_fn ao_kernel(int method, int samples)
+{
+	if (method == 0 && samples == 1) return ao_m0_n1::intersect;
+	if (method == 0 && samples == 2) return ao_m0_n2::intersect;
+	if (method == 0 && samples == 3) return ao_m0_n3::intersect;
+	if (method == 0 && samples == 4) return ao_m0_n4::intersect;
+	if (method == 1 && samples == 1) return ao_m1_n1::intersect;
+	if (method == 1 && samples == 2) return ao_m1_n2::intersect;
+	if (method == 1 && samples == 3) return ao_m1_n3::intersect;
+	if (method == 1 && samples == 4) return ao_m1_n4::intersect;
+	return nullptr;
+}
 
 #include "bvh.h"
 #include "compiler_options.h"
@@ -202,6 +283,40 @@ int ref_render(const orc_scene *sc, unsigned width, unsigned height, float focal
 			cl_compat_gid[1] = y;
 			if (shading) shaded::intersect(sc->faces, sc->nodes, aabbs, verts, norms, image);
 			else flat::intersect(sc->faces, sc->nodes, aabbs, verts, norms, image);
+		}
+	});
+	return 0;
+}
+
+/* The reference kernel with ambient occlusion (AO_ENABLE, intersect_kernel.cl:214-277, 305-307).
+ * method 0 = uniform rings, 1 = random hemisphere; samples in 1..4 (compiled copies).  Returns -2 for a
+ * (method, samples) pair that was not compiled. */
+int ref_render_ao(const orc_scene *sc, unsigned width, unsigned height, float focal_length, int method, int samples,
+                  float ao_max_distance, int alpha_min, int alpha_max,
+                  unsigned row_begin, unsigned row_end, unsigned row_step, float *image, int nthreads)
+{
+	if (!sc || !image || width == 0 || height == 0) return -1;
+	const ref_kernel_fn fn = ao_kernel(method, samples);
+	if (!fn) return -2;
+	if (row_step == 0) row_step = 1;
+	if (row_end > height) row_end = height;
+	if (row_begin >= row_end) return 0;
+	g_width = (int)width;
+	g_height = (int)height;
+	g_focal = focal_length;
+	g_ao_max_distance = ao_max_distance;
+	g_ao_alpha_min = alpha_min;
+	g_ao_alpha_max = alpha_max;
+	const float4 *aabbs = reinterpret_cast<const float4 *>(sc->aabbs);
+	const float4 *verts = reinterpret_cast<const float4 *>(sc->vertices);
+	const float4 *norms = reinterpret_cast<const float4 *>(sc->normals);
+	const unsigned nitems = (row_end - row_begin + row_step - 1) / row_step;
+	parallel_rows(nitems, nthreads, [&](unsigned item) {
+		const unsigned y = row_begin + item * row_step;
+		for (unsigned x = 0; x < width; ++x) {
+			cl_compat_gid[0] = x;
+			cl_compat_gid[1] = y;
+			fn(sc->faces, sc->nodes, aabbs, verts, norms, image);
 		}
 	});
 	return 0;

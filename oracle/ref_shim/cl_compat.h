@@ -53,12 +53,16 @@ static inline float clamp(float v, float lo, float hi) { return std::fmin(std::f
 static inline float max(float a, float b) { return a < b ? b : a; }
 static inline float min(float a, float b) { return b < a ? b : a; }
 static inline int max(int a, int b) { return a < b ? b : a; }
-static inline float cospi(float x) { return std::cos(3.14159265358979323846f * x); }
-static inline float sinpi(float x) { return std::sin(3.14159265358979323846f * x); }
-using std::acos;
-using std::cos;
+/* Transcendentals (only the ambient-occlusion samplers use them).  OpenCL leaves their last bits to the
+ * device (<= 4 ulp), so any definition is a legal reference; this one is chosen so that a CPU and a GPU can
+ * agree bit for bit: evaluate in double precision and round once to float (two double-precision libraries
+ * differ by far less than a float rounding step almost everywhere). */
+static inline float sin(float x) { return (float)std::sin((double)x); }
+static inline float cos(float x) { return (float)std::cos((double)x); }
+static inline float acos(float x) { return (float)std::acos((double)x); }
+static inline float cospi(float x) { return (float)std::cos((double)(3.14159265358979323846f * x)); }
+static inline float sinpi(float x) { return (float)std::sin((double)(3.14159265358979323846f * x)); }
 using std::fabs;
-using std::sin;
 using std::sqrt;
 
 /* work-item id of the "NDRange" the glue iterates */

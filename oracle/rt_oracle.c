@@ -210,6 +210,111 @@ static inline f4 get_smooth_normal(const orc_scene *sc, const isect_t *isect)
 		f4_mul(f4_load(sc->normals + 4 * (size_t)v2), bz)));
 }
 
+/* ---------------- ambient occlusion (intersect_kernel.cl:128-183, 214-277) ---------------- */
+
+/* Transcendentals: OpenCL leaves their last bits to the device; the oracle pins them as "evaluate in double,
+ * round once to float" (same definition in ref_shim/cl_compat.h and in the CUDA kernels). */
+static inline float t_sin(float x) { return (float)sin((double)x); }
+static inline float t_cos(float x) { return (float)cos((double)x); }
+static inline float t_acos(float x) { return (float)acos((double)x); }
+static inline float t_cospi(float x) { return (float)cos((double)(3.14159265358979323846f * x)); }
+static inline float t_sinpi(float x) { return (float)sin((double)(3.14159265358979323846f * x)); }
+
+static inline f4 f4_muls(f4 a, float s) { return f4_make(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+/* :128-135 xorshift128 */
+static inline uint32_t random_int(uint32_t v[4])
+{
+	const uint32_t t = v[0] ^ (v[0] << 11u);
+	v[0] = v[1]; v[1] = v[2]; v[2] = v[3];
+	return v[3] = v[3] ^ (v[3] >> 19u) ^ (t ^ (t >> 8u));
+}
+/* :136-142 */
+static inline void random_initialize_seed(uint32_t v[4], uint32_t seed)
+{
+	v[0] = (123456789u ^ seed) * 88675123u;
+	v[1] = (362436069u ^ seed) * 123456789u;
+	v[2] = (521288629u ^ seed) * 362436069u;
+	v[3] = (88675123u ^ seed) * 521288629u;
+	random_int(v);
+}
+/* :150-152 */
+static inline float random_float(uint32_t v[4]) { return 2.32830643653869629E-10f * (float)random_int(v); }
+
+/* the "replace the smallest component by 1" step shared by :156-164 and :226-234 */
+static inline f4 perturb_smallest(f4 h)
+{
+	if (fabsf(h.x) <= fabsf(h.y) && fabsf(h.x) <= fabsf(h.z)) h.x = 1.0f;
+	else if (fabsf(h.y) <= fabsf(h.x) && fabsf(h.y) <= fabsf(h.z)) h.y = 1.0f;
+	else if (fabsf(h.z) <= fabsf(h.x) && fabsf(h.z) <= fabsf(h.y)) h.z = 1.0f;
+	return h;
+}
+
+static inline int any_hit(const orc_scene *sc, f4 p, f4 dir, float max_distance, orc_counters *c)
+{
+	isect_t scratch;                       /* :249,:262,:269 pass an uninitialised Intersection; only the bool is used */
+	memset(&scratch, 0, sizeof scratch);
+	scratch.distance = INFINITY;
+	return scene_intersect(sc, p, dir, &scratch, max_distance, c);
+}
+
+/* :214-277 */
+static float ambient_occlusion(const orc_scene *sc, f4 point, f4 normal, uint32_t index, const orc_ao *ao, orc_counters *c)
+{
+	const f4 p = f4_add(point, f4_muls(normal, 1.0f / 100000.0f));                 /* :215 */
+	uint32_t hits = 0;
+	const float max_distance = ao->max_distance;                                    /* :217 */
+	if (ao->method == 0) {                                                          /* AO_METHOD_UNIFORM :218-256 */
+		uint32_t n = 0;
+		const uint32_t circle_count = ao->samples;
+		const float degrees = (float)(M_PI / 180);                                  /* :221 (M_PI is a double here) */
+		const float alpha_min = (float)ao->alpha_min * degrees;
+		const float alpha_max = (float)ao->alpha_max * degrees;
+		const f4 basis_y = normal;
+		const f4 h = perturb_smallest(basis_y);                                     /* :225-234 */
+		const f4 basis_x = f4_normalize(f4_cross(h, basis_y));
+		const f4 basis_z = f4_normalize(f4_cross(basis_x, basis_y));
+		for (uint32_t cc = 0; cc < circle_count; ++cc) {
+			const float step = alpha_max / (float)circle_count;                     /* :238 */
+			const float angle = (step * (float)cc) + alpha_min;                     /* :239 */
+			const uint32_t ray_count = (uint32_t)(((double)2.0f * M_PI * (double)t_cos(angle)) / (double)step); /* :240 */
+			const float theta = (float)(M_PI_2 - (double)angle);                    /* :241 */
+			for (uint32_t cr = 0; cr <= ray_count; ++cr) {                          /* :242 (<=) */
+				const float phi = (float)(((double)2.0f * M_PI * (double)cr) / (double)ray_count); /* :243 */
+				const float xs = t_sin(theta) * t_cospi(phi);
+				const float ys = t_cos(theta);
+				const float zs = t_sin(theta) * t_sinpi(phi);
+				const f4 ray_dir = f4_add(f4_add(f4_muls(basis_x, xs), f4_muls(basis_y, ys)), f4_muls(basis_z, zs)); /* :248 */
+				++n;
+				if (any_hit(sc, p, ray_dir, max_distance, c)) ++hits;
+			}
+		}
+		return 1.0f - ((float)hits / (float)n);                                     /* :256 */
+	}
+	/* AO_METHOD_RANDOM :257-275, sampler :153-183 */
+	const f4 basis_y = f4_normalize(normal);
+	const f4 h = perturb_smallest(basis_y);
+	const f4 basis_x = f4_normalize(f4_cross(h, basis_y));
+	const f4 basis_z = f4_normalize(f4_cross(basis_x, basis_y));
+	uint32_t rng[4];
+	random_initialize_seed(rng, 536870923u * index);                                /* :169 */
+	uint32_t n = ao->samples;
+	++n;                                                                            /* :263 */
+	if (any_hit(sc, p, normal, max_distance, c)) ++hits;                            /* :264 */
+	for (uint32_t i = 0; i < n; ++i) {                                              /* :267 */
+		const float xi1 = random_float(rng);
+		const float xi2 = random_float(rng);
+		const float theta = t_acos(sqrtf(1.0f - xi1));                              /* :175 */
+		const float phi = (float)(2.0 * (double)xi2);                               /* :177 */
+		const float xs = t_sin(theta) * t_cospi(phi);
+		const float ys = t_cos(theta);
+		const float zs = t_sin(theta) * t_sinpi(phi);
+		const f4 direction = f4_add(f4_add(f4_muls(basis_x, xs), f4_muls(basis_y, ys)), f4_muls(basis_z, zs));
+		if (any_hit(sc, p, f4_normalize(direction), max_distance, c)) ++hits;
+	}
+	return 1.0f - ((float)hits / (float)n);                                         /* :275 */
+}
+
 /* ---- extensions used only by configs C3 (jitter) and C5 (random rays) ---- */
 
 static inline uint32_t mix32(uint32_t x)
@@ -261,7 +366,7 @@ void orc_gen_random_rays(uint32_t seed, uint64_t first, size_t n, const float *b
 }
 
 /* intersect_kernel.cl:278-310 for one pixel. */
-static inline void pixel(const orc_scene *sc, int W, int H, float focal, int shading, uint32_t jitter_seed,
+static inline void pixel(const orc_scene *sc, int W, int H, float focal, int shading, uint32_t jitter_seed, const orc_ao *ao,
                          uint32_t x, uint32_t y, float *value, uint32_t *face_id, float *distance, orc_counters *c)
 {
 	const f4 camera_position = f4_make(0.0f, 0.0f, 2.0f, 0.0f);       /* :284 */
@@ -283,6 +388,8 @@ static inline void pixel(const orc_scene *sc, int W, int H, float focal, int sha
 	} else {
 		const f4 normal = get_smooth_normal(sc, &isect);              /* :301 */
 		if (shading) v = shade(ray_dir, normal);                      /* :302-304 */
+		if (ao && ao->enable && ao->samples > 0)                      /* :305-307; AO rays are not counted */
+			v *= ambient_occlusion(sc, isect.position, normal, y * (uint32_t)W + x, ao, NULL);
 	}
 	*value = v;                                                       /* :309 */
 	if (face_id) *face_id = hit ? isect.face_id : ORC_NO_HIT;
@@ -309,6 +416,7 @@ typedef struct job {
 	int mode;                    /* 0 render, 1 rays     */
 	/* render */
 	int W, H; float focal; int shading; uint32_t jitter_seed;
+	const orc_ao *ao;
 	unsigned row_begin, row_step;
 	float *image; uint32_t *face_id; float *distance;
 	/* rays */
@@ -343,7 +451,7 @@ static void *worker_main(void *arg)
 			const uint32_t y = jb->row_begin + (uint32_t)item * jb->row_step;
 			for (uint32_t x = 0; x < (uint32_t)jb->W; ++x) {
 				const size_t idx = (size_t)y * (size_t)jb->W + x;    /* :281 */
-				pixel(jb->sc, jb->W, jb->H, jb->focal, jb->shading, jb->jitter_seed, x, y,
+				pixel(jb->sc, jb->W, jb->H, jb->focal, jb->shading, jb->jitter_seed, jb->ao, x, y,
 				      jb->image + idx,
 				      jb->face_id ? jb->face_id + idx : NULL,
 				      jb->distance ? jb->distance + idx : NULL, c);
@@ -407,6 +515,14 @@ int orc_render(const orc_scene *scene, unsigned width, unsigned height, float fo
                uint32_t jitter_seed, unsigned row_begin, unsigned row_end, unsigned row_step,
                float *image, uint32_t *face_id, float *distance, orc_counters *counters, int nthreads)
 {
+	return orc_render_ao(scene, width, height, focal_length, shading, jitter_seed, NULL, row_begin, row_end, row_step,
+	                     image, face_id, distance, counters, nthreads);
+}
+
+int orc_render_ao(const orc_scene *scene, unsigned width, unsigned height, float focal_length, int shading,
+                  uint32_t jitter_seed, const orc_ao *ao, unsigned row_begin, unsigned row_end, unsigned row_step,
+                  float *image, uint32_t *face_id, float *distance, orc_counters *counters, int nthreads)
+{
 	if (!scene || !image || !scene->nodes || scene->nnodes == 0 || width == 0 || height == 0) return -1;
 	if (row_step == 0) row_step = 1;
 	if (row_end > height) row_end = height;
@@ -415,6 +531,7 @@ int orc_render(const orc_scene *scene, unsigned width, unsigned height, float fo
 	memset(&jb, 0, sizeof jb);
 	jb.sc = scene; jb.mode = 0;
 	jb.W = (int)width; jb.H = (int)height; jb.focal = focal_length; jb.shading = shading; jb.jitter_seed = jitter_seed;
+	jb.ao = ao;
 	jb.row_begin = row_begin; jb.row_step = row_step;
 	jb.nitems = (row_end - row_begin + row_step - 1) / row_step;
 	jb.image = image; jb.face_id = face_id; jb.distance = distance;

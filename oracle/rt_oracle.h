@@ -78,6 +78,23 @@ int orc_render(const orc_scene *scene, unsigned width, unsigned height,
                float *image, uint32_t *face_id, float *distance,
                orc_counters *counters, int nthreads);
 
+/* Ambient occlusion options of the kernel (opencl_host.cc:47-53: AO_ENABLE, AO_MAX_DISTANCE, AO_NUM_SAMPLES,
+ * AO_METHOD, AO_ALPHA_MIN, AO_ALPHA_MAX). */
+typedef struct orc_ao {
+	int      enable;
+	int      method;        /* 0 uniform rings (:218-256), 1 random hemisphere (:257-275) */
+	uint32_t samples;
+	float    max_distance;
+	int      alpha_min, alpha_max;
+} orc_ao;
+
+/* orc_render with the kernel's ambient-occlusion stage (intersect_kernel.cl:214-277, :305-307); ao may be NULL. */
+int orc_render_ao(const orc_scene *scene, unsigned width, unsigned height,
+                  float focal_length, int shading, uint32_t jitter_seed, const orc_ao *ao,
+                  unsigned row_begin, unsigned row_end, unsigned row_step,
+                  float *image, uint32_t *face_id, float *distance,
+                  orc_counters *counters, int nthreads);
+
 /* intersect_kernel.cl:184-213 for arbitrary rays (config C5).
  * origins/dirs: 4 floats per ray (w ignored = 0). */
 int orc_trace_rays(const orc_scene *scene, const float *origins,

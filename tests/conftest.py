@@ -86,3 +86,11 @@ def require_gpu():
     if host.device_count() == 0:
         pytest.fail("test marked gpu but no CUDA device is visible")
     return host
+
+
+@pytest.fixture(scope="session")
+def ao_golden():
+    return load_golden("soup_ao.npz")
+
+
+AO_CASES = ("uniform3", "random3", "random1_far", "uniform2_a10_60")

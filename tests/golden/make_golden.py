@@ -13,6 +13,8 @@ restatement or the CUDA path.  Outputs (small, committed):
   soup_rays.npz       4096 arbitrary rays (incl. axis-parallel ones) and their hits
   quad_33x17.npz      two big triangles sharing a diagonal, odd image size
   scenes.json         sha256 digests of the reference builder's arrays + bunny known answers
+  soup_ao.npz         the soup with ambient occlusion (uniform rings 3, random 3, random 1 with a longer reach);
+                      `python tests/golden/make_golden.py ao` writes only this file
 """
 import json
 import os
@@ -43,8 +45,28 @@ def render_case(sc, w, h, ss, focal=1.0, shading=True):
                 shading=int(shading))
 
 
+def make_ao():
+    """Ambient occlusion (intersect_kernel.cl:214-277, 305-307) through the reference's kernel text."""
+    v, f = scenes.random_soup(300, seed=11)
+    sc = ref_scene(v, f)
+    tw, th = po.ref_total_dims(32, 24, 4)
+    out = dict(verts=v, faces=f, width=32, height=24, nss=4)
+    for name, ao in (("uniform3", po.Ao.make(method=0, samples=3)), ("random3", po.Ao.make(method=1, samples=3)),
+                     ("random1_far", po.Ao.make(method=1, samples=1, max_distance=1.5)),
+                     ("uniform2_a10_60", po.Ao.make(method=0, samples=2, max_distance=0.7, alpha_min=10, alpha_max=60))):
+        img = po.ref_render_ao(sc, tw, th, ao, po.ref_focal_roundtrip(1.0))
+        out["image_" + name] = img
+        out["u8_" + name] = po.ref_resize(img, 32, 24, 4)
+        out["params_" + name] = np.array([ao.method, ao.samples, ao.alpha_min, ao.alpha_max], np.int32)
+        out["maxdist_" + name] = np.float32(ao.max_distance)
+    np.savez_compressed(os.path.join(OUT, "soup_ao.npz"), **out)
+    print("soup_ao.npz written")
+
+
 def main():
     assert po.ref() is not None, "oracle/_ref/libref_oracle.so missing: run make -C oracle"
+    if sys.argv[1:] == ["ao"]:
+        return make_ao()
     digests = {}
 
     v, f = scenes.random_soup(300, seed=11)
@@ -99,6 +121,7 @@ def main():
         json.dump(dict(digests=digests, bunny_c1=kat,
                        focal_roundtrip={str(x): po.ref_focal_roundtrip(x) for x in (1.0, 1.2345678, 0.5, 3.3333333, 0.001, 123456.789)}),
                   fh, indent=1, sort_keys=True)
+    make_ao()
     print("golden vectors written to", OUT)
 
 

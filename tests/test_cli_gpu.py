@@ -21,7 +21,7 @@ def read_pgm(path):
 
 
 @pytest.mark.gpu
-def test_reference_cli_writes_the_reference_pgm(tmp_path, scene_mod, soup_golden):
+def test_reference_cli_writes_the_reference_pgm(tmp_path, scene_mod, soup_golden, ao_golden):
     require_gpu()
     if not os.path.exists(CLI):
         pytest.skip("oracle/_ref/render_b200 not built (reference tree absent at build time)")
@@ -34,9 +34,13 @@ def test_reference_cli_writes_the_reference_pgm(tmp_path, scene_mod, soup_golden
     assert res.returncode == 0, res.stdout + res.stderr
     assert "Rendering image" in res.stdout and "Using Device" in res.stdout
     assert np.array_equal(read_pgm(pgm), g["u8"])
-    # ambient occlusion (the CLI default) is outside this path: the adapter reports it and exits non-zero
-    res = subprocess.run([CLI, "-w", "16", "-h", "16", off, pgm], capture_output=True, text=True, timeout=120)
-    assert res.returncode != 0 and "ambient occlusion" in (res.stdout + res.stderr)
+    # the CLI's defaults: ambient occlusion on (uniform, 3 rings, 0.2); and `-m random`, `-d`, `-a`
+    a = ao_golden
+    size = ["-w", str(int(a["width"])), "-h", str(int(a["height"])), "-s", str(int(a["nss"]))]
+    for extra, name in (([], "uniform3"), (["-m", "random"], "random3"), (["-m", "random", "-a", "1", "-d", "1.5"], "random1_far")):
+        res = subprocess.run([CLI] + size + extra + [off, pgm], capture_output=True, text=True, timeout=120)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert np.array_equal(read_pgm(pgm), a["u8_" + name]), name
 
 
 def test_reference_cli_fails_loudly_without_a_device(tmp_path, scene_mod, soup_golden):

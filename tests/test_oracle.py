@@ -133,3 +133,35 @@ def test_bunny_known_answers(po, bunny_scene, golden_meta):
     assert int((u8 != 0).sum()) == k["pgm_nonzero"] == 191727
     assert abs(r.counters["V"] - 26.98) < 0.01 and abs(r.counters["T"] - 2.014) < 0.001
     assert abs(po.algorithmic_bytes_per_ray(r.counters["V"], r.counters["T"], r.counters["h"]) - 989.5) < 0.5
+
+
+def _ao_of(po, g, name):
+    m, n, amin, amax = (int(x) for x in g["params_" + name])
+    return po.Ao.make(method=m, samples=n, max_distance=float(g["maxdist_" + name]), alpha_min=amin, alpha_max=amax)
+
+
+@pytest.mark.parametrize("name", ["uniform3", "random3", "random1_far", "uniform2_a10_60"])
+def test_port_matches_golden_ambient_occlusion(po, soup_scene, ao_golden, name):
+    """intersect_kernel.cl:214-277, 305-307 (both samplers) against the reference kernel text's output."""
+    g = ao_golden
+    n = int(np.sqrt(int(g["nss"])))
+    W, H = int(g["width"]) * n, int(g["height"]) * n
+    ao = _ao_of(po, g, name)
+    r = po.render(soup_scene, W, H, 1.0, True, ao=ao)
+    assert np.array_equal(_bits(r.image), _bits(g["image_" + name]))
+    assert np.array_equal(po.resize(r.image, int(g["width"]), int(g["height"]), n), g["u8_" + name])
+    plain = po.render(soup_scene, W, H, 1.0, True)
+    assert (r.image <= plain.image).all() and (r.image < plain.image).sum() > 50      # occlusion only darkens, and does
+    assert np.array_equal(r.face_id, plain.face_id)
+
+
+def test_ambient_occlusion_port_matches_reference_library_live(po, sibenik_scene):
+    """Where oracle/_ref/ exists: restatement == reference kernel text with AO_ENABLE on the interior scene
+    (the CLI's default options: uniform, 3 rings, 0.2, 4..90 degrees) and with the random sampler."""
+    if po.ref() is None:
+        pytest.skip("oracle/_ref/libref_oracle.so not present")
+    W, H = 96, 64
+    for ao in (po.Ao.make(), po.Ao.make(method=1, samples=4), po.Ao.make(method=0, samples=4, max_distance=2.0)):
+        r = po.render(sibenik_scene, W, H, 1.0, True, ao=ao)
+        img = po.ref_render_ao(sibenik_scene, W, H, ao)
+        assert np.array_equal(_bits(r.image), _bits(img))

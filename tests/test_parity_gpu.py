@@ -362,8 +362,11 @@ def test_error_behaviour(soup_scene):
         h.upload_scene(soup_scene)
         assert h() is True
     with pytest.raises(host.RtxError) as e:
-        host.CudaHost(host.RayTracer(host.Options(enableAO=True, aoNumSamples=3)))
-    assert e.value.code == host.ERR_UNSUPPORTED
+        host.CudaHost(host.RayTracer(host.Options(enableAO=True, aoNumSamples=3, aoMethod=7)))
+    assert e.value.code == host.ERR_ARG
+    with pytest.raises(host.RtxError) as e:
+        host.CudaHost(host.RayTracer(host.Options(enableAO=True, aoNumSamples=3, aoAlphaMax=0)))
+    assert e.value.code == host.ERR_ARG
     with pytest.raises(host.RtxError) as e:
         host.CudaHost(rt, device=99)
     assert e.value.code == host.ERR_NO_DEVICE
