@@ -1178,13 +1178,39 @@ __device__ __noinline__ bool walk_reference_any(const SceneDev &sc, f3 o, f3 d, 
 	return false;
 }
 
-RTX_DEV bool any_hit(const SceneDev &sc, bool ordered_ok, f3 o, f3 d, float max_distance)
+/* All occlusion rays of a pixel leave the same point p and a box is only entered with t_min < max_distance
+ * (:60), i.e. within max_distance * |d| of p, |d| = 1 up to a few ulp (normalised bases, xs^2+ys^2+zs^2 = 1).
+ * So only leaves whose box reaches into the cube p +- R, R = max_distance * 1.001 + 1e-5 * scale, can pass
+ * (a box beyond the cube along axis k has t_k,min >= R / |d_k| > max_distance when d_k points towards it and
+ * t_max < 0 when it points away; margins are 4 orders above the rounding of the slab products).  Walk down
+ * from the root while exactly one child reaches into the cube: the rays of the pixel start at that pair
+ * instead of the root.  -1: no leaf can pass at all. */
+RTX_DEV int ao_entry_pair(const SceneDev &sc, f3 p, float max_distance)
+{
+	const float R = max_distance * 1.001f + 1e-5f * fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fmaxf(fabsf(p.z), sc.scene_scale));
+	if (!(R == R) || !(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z)) return 0;
+	const f3 lo = make_f3(p.x - R, p.y - R, p.z - R), hi = make_f3(p.x + R, p.y + R, p.z + R);
+	int cur = 0;
+	for (;;) {
+		const float4 *q = sc.pairs + 4 * (size_t)cur;
+		const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+		const bool inL = q0.x <= hi.x && q0.w >= lo.x && q0.y <= hi.y && q1.x >= lo.y && q0.z <= hi.z && q1.y >= lo.z;
+		const bool inR = q2.x <= hi.x && q2.w >= lo.x && q2.y <= hi.y && q3.x >= lo.y && q2.z <= hi.z && q3.y >= lo.z;
+		if (inL == inR) return inL ? cur : -1;
+		const int ref = __float_as_int(inL ? q1.z : q3.z);
+		if (ref < 0) return cur;                 /* the one child is a leaf: its parent pair is the entry */
+		cur = ref;
+	}
+}
+
+RTX_DEV bool any_hit(const SceneDev &sc, bool ordered_ok, int entry, f3 o, f3 d, float max_distance)
 {
 	const bool plain = d.x != 0.0f && d.y != 0.0f && d.z != 0.0f && d.x == d.x && d.y == d.y && d.z == d.z;
 	if (!(ordered_ok && plain)) return walk_reference_any(sc, o, d, max_distance);
+	if (entry < 0) return false;
 	const f3 id = make_f3(rn_div(1.0f, d.x), rn_div(1.0f, d.y), rn_div(1.0f, d.z));
 	int stack[RTX_STACK_MAX];
-	int sp = 0, cur = 0;
+	int sp = 0, cur = entry;
 	for (;;) {
 		while (cur >= 0) {
 			const float4 *q = sc.pairs + 4 * (size_t)cur;
@@ -1251,6 +1277,7 @@ RTX_DEV float ambient_occlusion(const SceneDev &sc, bool ordered_ok, f3 point, f
 {
 	const float k = rn_div(1.0f, 100000.0f);
 	const f3 p = make_f3(rn_add(point.x, rn_mul(normal.x, k)), rn_add(point.y, rn_mul(normal.y, k)), rn_add(point.z, rn_mul(normal.z, k))); /* :215 */
+	const int entry = ordered_ok ? ao_entry_pair(sc, p, ao.max_distance) : 0;
 	uint32_t hits = 0;
 	if (ao.method == 0) {                                                    /* :218-256 */
 		const f3 basis_y = normal;
@@ -1262,7 +1289,7 @@ RTX_DEV float ambient_occlusion(const SceneDev &sc, bool ordered_ok, f3 point, f
 		for (uint32_t i = 0; i < n; ++i) {
 			const float4 s = __ldg(ao.ring + 1 + i);
 			const f3 dir = combine3(basis_x, s.x, basis_y, s.y, basis_z, s.z);   /* :248 */
-			if (any_hit(sc, ordered_ok, p, dir, ao.max_distance)) ++hits;
+			if (any_hit(sc, ordered_ok, entry, p, dir, ao.max_distance)) ++hits;
 		}
 		return rn_sub(1.0f, rn_div((float)hits, (float)n));                  /* :256 */
 	}
@@ -1279,7 +1306,7 @@ RTX_DEV float ambient_occlusion(const SceneDev &sc, bool ordered_ok, f3 point, f
 	rng[3] = (88675123u ^ seed) * 521288629u;
 	ao_random_int(rng);
 	const uint32_t n = ao.samples + 1u;
-	if (any_hit(sc, ordered_ok, p, normal, ao.max_distance)) ++hits;
+	if (any_hit(sc, ordered_ok, entry, p, normal, ao.max_distance)) ++hits;
 	for (uint32_t i = 0; i < n; ++i) {
 		const float xi1 = ao_random_float(rng);
 		const float xi2 = ao_random_float(rng);
@@ -1289,7 +1316,7 @@ RTX_DEV float ambient_occlusion(const SceneDev &sc, bool ordered_ok, f3 point, f
 		const float ys = t_cos(theta);
 		const float zs = rn_mul(t_sin(theta), t_sinpi(phi));
 		const f3 dir = normalize3(combine3(basis_x, xs, basis_y, ys, basis_z, zs));
-		if (any_hit(sc, ordered_ok, p, dir, ao.max_distance)) ++hits;
+		if (any_hit(sc, ordered_ok, entry, p, dir, ao.max_distance)) ++hits;
 	}
 	return rn_sub(1.0f, rn_div((float)hits, (float)n));
 }

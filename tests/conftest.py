@@ -93,4 +93,4 @@ def ao_golden():
     return load_golden("soup_ao.npz")
 
 
-AO_CASES = ("uniform3", "random3", "random1_far", "uniform2_a10_60")
+AO_CASES = ("uniform3", "random3", "random1_far", "uniform2_a10_60", "uniform2_d07")

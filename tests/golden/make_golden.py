@@ -53,7 +53,8 @@ def make_ao():
     out = dict(verts=v, faces=f, width=32, height=24, nss=4)
     for name, ao in (("uniform3", po.Ao.make(method=0, samples=3)), ("random3", po.Ao.make(method=1, samples=3)),
                      ("random1_far", po.Ao.make(method=1, samples=1, max_distance=1.5)),
-                     ("uniform2_a10_60", po.Ao.make(method=0, samples=2, max_distance=0.7, alpha_min=10, alpha_max=60))):
+                     ("uniform2_a10_60", po.Ao.make(method=0, samples=2, max_distance=0.7, alpha_min=10, alpha_max=60)),
+                     ("uniform2_d07", po.Ao.make(method=0, samples=2, max_distance=0.7))):
         img = po.ref_render_ao(sc, tw, th, ao, po.ref_focal_roundtrip(1.0))
         out["image_" + name] = img
         out["u8_" + name] = po.ref_resize(img, 32, 24, 4)

@@ -34,10 +34,12 @@ def test_reference_cli_writes_the_reference_pgm(tmp_path, scene_mod, soup_golden
     assert res.returncode == 0, res.stdout + res.stderr
     assert "Rendering image" in res.stdout and "Using Device" in res.stdout
     assert np.array_equal(read_pgm(pgm), g["u8"])
-    # the CLI's defaults: ambient occlusion on (uniform, 3 rings, 0.2); and `-m random`, `-d`, `-a`
+    # the CLI's defaults: ambient occlusion on (uniform, 3 rings, 0.2); and `-a`, `-d`.  (`-m` and `-r` cannot be
+    # exercised: the reference's own args.h:216-233 returns a reference to a dead temporary from map() and the
+    # unmodified parser segfaults on either option under gcc 13 -O2, before any device code runs.)
     a = ao_golden
     size = ["-w", str(int(a["width"])), "-h", str(int(a["height"])), "-s", str(int(a["nss"]))]
-    for extra, name in (([], "uniform3"), (["-m", "random"], "random3"), (["-m", "random", "-a", "1", "-d", "1.5"], "random1_far")):
+    for extra, name in (([], "uniform3"), (["-a", "2", "-d", "0.7"], "uniform2_d07")):
         res = subprocess.run([CLI] + size + extra + [off, pgm], capture_output=True, text=True, timeout=120)
         assert res.returncode == 0, res.stdout + res.stderr
         assert np.array_equal(read_pgm(pgm), a["u8_" + name]), name

@@ -140,7 +140,7 @@ def _ao_of(po, g, name):
     return po.Ao.make(method=m, samples=n, max_distance=float(g["maxdist_" + name]), alpha_min=amin, alpha_max=amax)
 
 
-@pytest.mark.parametrize("name", ["uniform3", "random3", "random1_far", "uniform2_a10_60"])
+@pytest.mark.parametrize("name", ["uniform3", "random3", "random1_far", "uniform2_a10_60", "uniform2_d07"])
 def test_port_matches_golden_ambient_occlusion(po, soup_scene, ao_golden, name):
     """intersect_kernel.cl:214-277, 305-307 (both samplers) against the reference kernel text's output."""
     g = ao_golden
