@@ -158,6 +158,11 @@ int rtx_get_stats(const rtx_ctx *ctx, rtx_stats *stats);
 int rtx_render_async(rtx_ctx *ctx, void *stream);
 int rtx_synchronize(rtx_ctx *ctx);
 
+/* rtx_render + rtx_download in one blocking call (whole image only): the frame is traced in bands of tile
+ * rows and every finished band is copied to `image` on a second stream while the next one is traced.  `image`
+ * should be page-locked for the copies to overlap (pageable memory works, without the overlap). */
+int rtx_render_download(rtx_ctx *ctx, float *image);
+
 /* Per-ray hit triangle (3 * leaf index, the kernel's face_id; RTX_NO_HIT on
  * miss) and hit distance (+inf on miss) of the last render; needs
  * RTX_TUNE_RECORD_HITS.  Whole image only. */

@@ -49,12 +49,16 @@ struct DevBuf {
 
 } /* namespace */
 
+#define RTX_MAX_BANDS 16
+
 struct rtx_ctx {
 	rtx_options opt;
 	float focal;                 /* after the compiler_options.h round trip */
 	int device = 0;
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copy_stream = nullptr;                 /* rtx_render_download: device->host copies of finished bands */
+	cudaEvent_t band_ev[RTX_MAX_BANDS] = {}, copy_done = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	bool ev_pending = false;
 	std::string error;
@@ -544,6 +548,9 @@ void rtx_destroy(rtx_ctx *c)
 	for (DevBuf *b : bufs) b->release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
+	for (cudaEvent_t e : c->band_ev) if (e) cudaEventDestroy(e);
+	if (c->copy_done) cudaEventDestroy(c->copy_done);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -718,7 +725,10 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	return RTX_OK;
 }
 
-static int enqueue_render(rtx_ctx *c, cudaStream_t st)
+/* host_dst != NULL (rtx_render_download, whole image only): the frame is rendered in bands of tile rows and each
+ * finished band -- a contiguous row range of the row-major image -- is copied to the host on a second stream
+ * while the next band renders, so the device->host copy (the longer of the two at PCIe rates) hides the tracing. */
+static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr)
 {
 	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
 	if (!c->uploaded) return fail(c, RTX_ERR_STATE, "render before upload");
@@ -754,6 +764,8 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 	w.rank = c->rank;
 	w.world = c->world;
 	w.local_tiles = c->local_tiles;
+	w.tile_begin = 0;
+	w.tile_count = c->local_tiles;
 	w.num_units = c->local_tiles * 32u;
 	w.counter = c->d_counter.as<unsigned int>();
 	w.image = c->ext_image ? c->ext_image : c->d_image.as<float>();
@@ -786,9 +798,45 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 		}
 		k_frustum_collect<<<(c->local_tiles + 7) / 8, 256, 0, st>>>(c->sc, w, two_level ? c->d_slists.as<uint32_t>() : nullptr, c->d_lists.as<uint32_t>());
 		CU(c, cudaGetLastError());
-		c->stats.kernel_launches = (two_level ? 4 : 3) + table_launch;
+		c->stats.kernel_launches = (two_level ? 2 : 1) + table_launch;
+	} else {
+		c->stats.kernel_launches = table_launch;
 	}
-	CU(c, launch_render(c, w, st));
+	const uint32_t launches_per_pass = w.frustum ? 2u : 1u;
+	const size_t frame_bytes = (size_t)c->W * c->H * sizeof(float);
+	uint32_t nbands = 1;
+	if (host_dst && !c->ao && c->local_tiles > 0) {
+		nbands = (uint32_t)(frame_bytes / (8u << 20));             /* >= 8 MB per copy keeps PCIe near its rate */
+		if (nbands > RTX_MAX_BANDS) nbands = RTX_MAX_BANDS;
+		if (nbands > c->tiles_y) nbands = c->tiles_y;
+		if (nbands < 1) nbands = 1;
+	}
+	if (host_dst && nbands > 1) {
+		if (!c->copy_stream) CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+		if (!c->copy_done) CU(c, cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
+		for (uint32_t b = 0; b < nbands; ++b)
+			if (!c->band_ev[b]) CU(c, cudaEventCreateWithFlags(&c->band_ev[b], cudaEventDisableTiming));
+		const float *src = w.image;
+		for (uint32_t b = 0; b < nbands; ++b) {
+			const uint32_t r0 = (uint32_t)((uint64_t)c->tiles_y * b / nbands), r1 = (uint32_t)((uint64_t)c->tiles_y * (b + 1) / nbands);
+			w.tile_begin = r0 * c->tiles_x;
+			w.tile_count = (r1 - r0) * c->tiles_x;
+			w.num_units = w.tile_count * 32u;
+			if (b > 0) CU(c, cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st));   /* the work counter only */
+			CU(c, launch_render(c, w, st));
+			CU(c, cudaEventRecord(c->band_ev[b], st));
+			CU(c, cudaStreamWaitEvent(c->copy_stream, c->band_ev[b], 0));
+			const size_t y0 = (size_t)r0 * RTX_TILE, y1 = std::min<size_t>((size_t)r1 * RTX_TILE, c->H);
+			CU(c, cudaMemcpyAsync(host_dst + y0 * c->W, src + y0 * c->W, (y1 - y0) * c->W * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+		}
+		CU(c, cudaEventRecord(c->copy_done, c->copy_stream));
+		w.tile_begin = 0;
+		w.tile_count = c->local_tiles;
+		w.num_units = c->local_tiles * 32u;
+	} else {
+		CU(c, launch_render(c, w, st));
+	}
+	c->stats.kernel_launches += launches_per_pass * nbands;
 	uint32_t ao_launches = 0;
 	if (c->ao && w.num_units > 0) {
 		/* second pass over the hit pixels (intersect_kernel.cl:305-307) */
@@ -811,10 +859,13 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st)
 		++ao_launches;
 	}
 	CU(c, cudaEventRecord(c->ev1, st));
+	if (host_dst) {
+		if (nbands > 1) CU(c, cudaStreamWaitEvent(st, c->copy_done, 0));     /* `st` is done when the copies are */
+		else CU(c, cudaMemcpyAsync(host_dst, w.image, frame_bytes, cudaMemcpyDeviceToHost, st));
+	}
 	c->ev_pending = true;
 	c->stats.rays = (uint64_t)c->local_tiles * RTX_TILE * RTX_TILE;
 	if (c->world == 1) c->stats.rays = (uint64_t)c->W * c->H;
-	if (!w.frustum) c->stats.kernel_launches = 1 + table_launch;
 	c->stats.kernel_launches += ao_launches;
 	c->stats.kernel_variant = (c->kernel == RTX_KERNEL_EXHAUSTIVE || !w.ordered_ok) ? RTX_KERNEL_EXHAUSTIVE : RTX_KERNEL_PERSISTENT;
 	c->rendered = true;
@@ -841,6 +892,17 @@ int rtx_render(rtx_ctx *c)
 	const int rc = enqueue_render(c, c ? c->stream : nullptr);
 	if (rc != RTX_OK) return rc;
 	CU(c, cudaStreamSynchronize(c->stream));   /* queue.finish(), opencl_host.cc:147 */
+	return finish_stats(c);
+}
+
+/* operator()() + download() (opencl_host.cc:137-153) as one call, the copy overlapped with the tracing. */
+int rtx_render_download(rtx_ctx *c, float *image)
+{
+	if (!c || !image) return fail(c, RTX_ERR_ARG, "null argument");
+	if (c->world > 1) return fail(c, RTX_ERR_STATE, "this rank holds a tile partition; gather and de-interleave first");
+	const int rc = enqueue_render(c, c->stream, image);
+	if (rc != RTX_OK) return rc;
+	CU(c, cudaStreamSynchronize(c->stream));
 	return finish_stats(c);
 }
 

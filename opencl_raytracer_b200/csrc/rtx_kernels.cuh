@@ -259,7 +259,9 @@ struct Work {
 	uint32_t tiles_x, tiles_y;
 	uint32_t rank, world;
 	uint32_t local_tiles;        /* tiles this rank renders */
-	uint32_t num_units;          /* local_tiles * 32 */
+	uint32_t tile_begin, tile_count; /* the local tiles THIS launch renders (a band of tile rows when the download is
+	                                    pipelined, rtx_render_download; otherwise 0, local_tiles) */
+	uint32_t num_units;          /* tile_count * 32 */
 	unsigned int *counter;       /* persistent-kernel work counter (zeroed before launch) */
 	float *image;                /* world == 1: row-major W x H; else compact [local_tile][32][32] */
 	uint32_t *face_id;           /* optional (record mode), same indexing as image */
@@ -323,7 +325,7 @@ k_render_persistent(const SceneDev sc, const Work w, Counters *cnt)
 		if (unit >= w.num_units) break;
 		uint32_t x, y;
 		size_t out;
-		if (unit_pixel(w, unit, lane, x, y, out))
+		if (unit_pixel(w, unit + w.tile_begin * 32u, lane, x, y, out))
 			trace_pixel<SMEM_STACK, TOP_SMEM, COUNT, RECORD>(sc, w, s_top, s_stack, x, y, out, cnt);
 		__syncwarp();
 	}
@@ -727,8 +729,8 @@ k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 		uint32_t unit = 0;
 		if (lane == 0) unit = atomicAdd(w.counter, 1u);
 		unit = __shfl_sync(0xffffffffu, unit, 0);
-		if (unit >= w.local_tiles * UPT) break;
-		const uint32_t ltile = unit / UPT, sub = unit % UPT;
+		if (unit >= w.tile_count * UPT) break;
+		const uint32_t ltile = w.tile_begin + unit / UPT, sub = unit % UPT;
 		int nlist = -1;
 		if (MODE != 0) {
 			nlist = (int)__ldg(w.lists + (size_t)ltile * RTX_LIST_STRIDE);
@@ -815,7 +817,7 @@ k_render_exhaustive(const SceneDev sc, const Work w, Counters *cnt)
 	if (unit >= w.num_units) return;
 	uint32_t x, y;
 	size_t out;
-	if (!unit_pixel(w, unit, threadIdx.x & 31u, x, y, out)) return;
+	if (!unit_pixel(w, unit + w.tile_begin * 32u, threadIdx.x & 31u, x, y, out)) return;
 	const f3 o = make_f3(0.0f, 0.0f, 2.0f);
 	const f3 d = primary_dir(w.cam, x, y);
 	HitRec best;
@@ -979,7 +981,7 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 						r.index = idx;
 					} else {
 						uint32_t x, y;
-						valid = unit_pixel(pw, (uint32_t)(idx >> 5), (uint32_t)(idx & 31ull), x, y, out);
+						valid = unit_pixel(pw, (uint32_t)(idx >> 5) + pw.tile_begin * 32u, (uint32_t)(idx & 31ull), x, y, out);
 						r.o = make_f3(0.0f, 0.0f, 2.0f);
 						r.d = primary_dir(pw.cam, x, y);
 						r.max_distance = 100000.0f;
@@ -1329,7 +1331,7 @@ k_ambient_occlusion(const SceneDev sc, const Work w, const AoParams ao)
 	if (unit >= w.num_units) return;
 	uint32_t x, y;
 	size_t out;
-	if (!unit_pixel(w, unit, threadIdx.x & 31u, x, y, out)) return;
+	if (!unit_pixel(w, unit + w.tile_begin * 32u, threadIdx.x & 31u, x, y, out)) return;
 	const uint32_t fid = w.face_id[out];
 	if (fid == 0xffffffffu) return;
 	const uint32_t tri = fid / 3u;

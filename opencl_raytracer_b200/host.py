@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "rtx_download", "rtx_destroy", "rtx_last_error", "rtx_set_tunable", "rtx_get_stats", "rtx_render_async",
     "rtx_synchronize", "rtx_download_hits", "rtx_download_u8", "rtx_device_image", "rtx_trace_rays",
     "rtx_trace_rays_device", "rtx_trace_random_rays", "rtx_tile_layout", "rtx_deinterleave_async", "rtx_bind_output",
-    "rtx_probe_bandwidth", "rtx_resize_u8_async", "rtx_deinterleave_u8_async",
+    "rtx_probe_bandwidth", "rtx_resize_u8_async", "rtx_deinterleave_u8_async", "rtx_render_download",
 )
 
 
@@ -114,6 +114,8 @@ def load_library():
     lib.rtx_render_async.argtypes = [vp, vp]
     lib.rtx_synchronize.restype = C.c_int
     lib.rtx_synchronize.argtypes = [vp]
+    lib.rtx_render_download.restype = C.c_int
+    lib.rtx_render_download.argtypes = [vp, fp]
     lib.rtx_download_hits.restype = C.c_int
     lib.rtx_download_hits.argtypes = [vp, u32p, fp]
     lib.rtx_download_u8.restype = C.c_int
@@ -273,6 +275,14 @@ class CudaHost:
         return out
 
     # -- extensions --
+    def render_download(self, out: np.ndarray | None = None) -> np.ndarray:
+        """``__call__`` + ``download`` in one call, the device->host copy overlapped with the tracing band by band."""
+        if out is None:
+            out = np.empty((self.rt.totalHeight, self.rt.totalWidth), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.rt.totalWidth * self.rt.totalHeight
+        self._ck(self._lib.rtx_render_download(self._ctx, out.ctypes.data))
+        return out
+
     def set_tunable(self, which: int, value: int):
         self._ck(self._lib.rtx_set_tunable(self._ctx, which, value))
 

@@ -370,3 +370,35 @@ def test_error_behaviour(soup_scene):
     with pytest.raises(host.RtxError) as e:
         host.CudaHost(rt, device=99)
     assert e.value.code == host.ERR_NO_DEVICE
+
+
+@pytest.mark.parametrize("frustum,rpt", [(-1, 1), (0, 1), (0, 0), (0, 4)])
+def test_render_download_pipelined(po, sibenik_scene, soup_scene, frustum, rpt):
+    """rtx_render_download = operator()() + download(): bands of tile rows traced and copied on two streams.
+    3840x2160 floats = 33 MB -> 4 bands; the small frame takes the single-band path; AO falls back to one band."""
+    import torch
+    host = require_gpu()
+    rt = host.RayTracer(host.Options(width=1920, height=1080, nSuperSamples=4))
+    with host.CudaHost(rt) as h:
+        h.set_tunable(host.TUNE_FRUSTUM, frustum)
+        h.set_tunable(host.TUNE_RAYS_PER_THREAD, rpt)
+        h.upload_scene(sibenik_scene)
+        h()
+        want = h.download()
+        launches = h.stats()["kernel_launches"]
+        pinned = torch.empty((rt.totalHeight, rt.totalWidth), dtype=torch.float32).pin_memory().numpy()
+        pinned[:] = -1.0
+        got = h.render_download(pinned)
+        assert np.array_equal(got, want)
+        assert h.stats()["kernel_launches"] > launches                    # several bands
+        assert np.array_equal(h.render_download(), want)                  # pageable destination
+        assert np.array_equal(h.download(), want)                         # the device image is complete too
+    rt = host.RayTracer(host.Options(width=101, height=77, nSuperSamples=1))
+    with host.CudaHost(rt) as h:
+        h.upload_scene(soup_scene)
+        assert np.array_equal(h.render_download(), po.render(soup_scene, 101, 77, 1.0, True).image)
+    ao = po.Ao.make(method=1, samples=2, max_distance=0.6)
+    rt = host.RayTracer(host.Options(width=64, height=48, nSuperSamples=4, enableAO=True, aoNumSamples=2, aoMethod=1, aoMaxDistance=0.6))
+    with host.CudaHost(rt) as h:
+        h.upload_scene(soup_scene)
+        assert np.array_equal(h.render_download(), po.render(soup_scene, 128, 96, 1.0, True, ao=ao).image)
