@@ -170,7 +170,7 @@ void flatten(const uint32_t *nodes, const float *aabbs16, size_t n, int leaf_siz
 	auto box = [&](uint32_t node, float4 &a, float4 &b, int ref) {
 		const float *lo = aabbs16 + 8 * (size_t)node, *hi = lo + 4;
 		a = make_float4(lo[0], lo[1], lo[2], hi[0]);
-		b = make_float4(hi[1], hi[2], __builtin_bit_cast(float, ref), 0.0f);
+		b = make_float4(hi[1], hi[2], __builtin_bit_cast(float, ref), box_slack(lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]));
 	};
 	out.pairs.clear();
 	out.pairs.reserve(4 * (ntris / (size_t)std::max(1, leaf_size) + 16));

@@ -103,6 +103,20 @@ __device__ __noinline__ void walk_reference(const SceneDev &sc, f3 o, f3 d, floa
  * ------------------------------------------------------------------------ */
 struct Slab { float tmin, tmax; };
 
+/* Culling slack of a box, stored in the pad lane of its 32-byte node.  The reference accepts a hit whose
+ * parametric coordinates lie up to 1e-5 outside the triangle (intersect_kernel.cl:96,101), i.e. up to ~1e-5 of
+ * the triangle's extent outside its leaf box, so the ray can hit the triangle at parameter r and enter the
+ * triangle's box only LATER, at r + overshoot / |d_k| along the axis k it overshoots.  A box may therefore be
+ * skipped against the best hit so far only if  t_min - slack * max_k |1 / d_k|  lies beyond the culling bound,
+ * with slack >= the overshoot of any triangle inside: 2.5e-4 of the box's largest extent (25 x the nominal
+ * tolerance, for the rounding of s and t on thin triangles) + 4e-6 of its largest coordinate (rounding of P). */
+__host__ __device__ __forceinline__ float box_slack(float lx, float ly, float lz, float hx, float hy, float hz)
+{
+	const float ext = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz);
+	const float mag = fmaxf(fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy))), fmaxf(fabsf(lz), fabsf(hz)));
+	return 2.5e-4f * ext + 4e-6f * mag;
+}
+
 /* Slab interval of one box.  Same products as the literal test ((bb - o) * (1/d), one rounding each);
  * which of the two products per axis is the entry is decided
  *   OCT = 0 : by the data -- the warp reads the copy of the pair array whose x/y slots were swapped at
@@ -146,7 +160,7 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ pai
 	 * reference's max_distance (intersect_kernel.cl:60); triangles do not -- the reference accepts a
 	 * hit at any distance once its leaf box passed. */
 	float cull = __int_as_float(0x7f800000);
-	float limit = max_distance;          /* = min(max_distance, cull), for boxes */
+	const float maxid = fminf(fmaxf(fmaxf(fabsf(id.x), fabsf(id.y)), fabsf(id.z)), 1e30f);   /* see box_slack */
 	uint2 l_stack[RTX_STACK_MAX - SMEM_STACK];
 	int sp = 0;
 	int cur = 0;                         /* root pair */
@@ -167,13 +181,14 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ pai
 			if (COUNT) visits += 2;
 			const Slab L = slab_interval<PRIMARY, OCT>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, id);
 			const Slab R = slab_interval<PRIMARY, OCT>(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, o, id);
-			const bool hitL = L.tmin <= L.tmax && L.tmin < limit && L.tmax > 0.0f;
-			const bool hitR = R.tmin <= R.tmax && R.tmin < limit && R.tmax > 0.0f;
+			const float cL = __fmaf_rn(-q1.w, maxid, L.tmin), cR = __fmaf_rn(-q3.w, maxid, R.tmin);   /* entry, less the slack */
+			const bool hitL = L.tmin <= L.tmax && L.tmin < max_distance && cL < cull && L.tmax > 0.0f;
+			const bool hitR = R.tmin <= R.tmax && R.tmin < max_distance && cR < cull && R.tmax > 0.0f;
 			if (!(hitL || hitR)) goto pop;
 			const int refL = __float_as_int(q1.z), refR = __float_as_int(q3.z);
 			const bool r_first = hitR && (!hitL || R.tmin < L.tmin);
 			if (hitL && hitR) {
-				const uint2 e = make_uint2((uint32_t)(r_first ? refL : refR), __float_as_uint(r_first ? L.tmin : R.tmin));
+				const uint2 e = make_uint2((uint32_t)(r_first ? refL : refR), __float_as_uint(r_first ? cL : cR));
 				if (SMEM_STACK > 0 && sp < SMEM_STACK) s_stack[sp * stride] = e; else l_stack[sp - SMEM_STACK] = e;
 				++sp;
 			}
@@ -199,7 +214,6 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ pai
 				/* hits are accepted in decreasing distance, so this is the smallest so far; its ray
 				 * parameter is recovered from the distance (|P-o| = r|d| up to rounding) */
 				cull = (h.dist * inv_len) * 1.0001f + abs_margin;
-				limit = fminf(max_distance, cull);
 			}
 		}
 pop:
@@ -207,7 +221,7 @@ pop:
 			if (sp == 0) goto done;
 			--sp;
 			const uint2 e = (SMEM_STACK > 0 && sp < SMEM_STACK) ? s_stack[sp * stride] : l_stack[sp - SMEM_STACK];
-			if (__uint_as_float(e.y) < limit) { cur = (int)e.x; break; }
+			if (__uint_as_float(e.y) < cull) { cur = (int)e.x; break; }
 		}
 	}
 done:
@@ -351,12 +365,12 @@ RTX_DEV void traverse_packet(const SceneDev &sc, const float4 *__restrict__ pair
 	const float max_distance = 100000.0f;                              /* intersect_kernel.cl:292 */
 	const f3 o = make_f3(0.0f, 0.0f, 2.0f);                            /* :284 */
 	f3 id[NR];
-	float cull[NR], limit[NR];
+	float cull[NR], maxid[NR];
 #pragma unroll
 	for (int r = 0; r < NR; ++r) {
 		id[r] = make_f3(rn_div(1.0f, d[r].x), rn_div(1.0f, d[r].y), rn_div(1.0f, d[r].z));
-		cull[r] = __int_as_float(0x7f800000);
-		limit[r] = (active >> r) & 1u ? max_distance : __int_as_float(0xff800000);   /* -inf: enters nothing */
+		cull[r] = (active >> r) & 1u ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);   /* -inf: enters nothing */
+		maxid[r] = fminf(fmaxf(fmaxf(fabsf(id[r].x), fabsf(id[r].y)), fabsf(id[r].z)), 1e30f);       /* see box_slack */
 	}
 	const float abs_margin = 1e-5f * fmaxf(2.0f, sc.scene_scale);     /* |d| = 1 */
 	uint2 l_stack[RTX_STACK_MAX - SMEM_STACK];
@@ -378,10 +392,11 @@ RTX_DEV void traverse_packet(const SceneDev &sc, const float4 *__restrict__ pair
 			for (int r = 0; r < NR; ++r) {
 				const Slab L = slab_interval<true, OCT>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, id[r]);
 				const Slab R = slab_interval<true, OCT>(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, o, id[r]);
-				const bool hl = L.tmin <= L.tmax && L.tmin < limit[r] && L.tmax > 0.0f;
-				const bool hr = R.tmin <= R.tmax && R.tmin < limit[r] && R.tmax > 0.0f;
-				if (hl) { mL |= 1u << r; tL = fminf(tL, L.tmin); }
-				if (hr) { mR |= 1u << r; tR = fminf(tR, R.tmin); }
+				const float cl = __fmaf_rn(-q1.w, maxid[r], L.tmin), cr = __fmaf_rn(-q3.w, maxid[r], R.tmin);
+				const bool hl = L.tmin <= L.tmax && L.tmin < max_distance && cl < cull[r] && L.tmax > 0.0f;
+				const bool hr = R.tmin <= R.tmax && R.tmin < max_distance && cr < cull[r] && R.tmax > 0.0f;
+				if (hl) { mL |= 1u << r; tL = fminf(tL, cl); }
+				if (hr) { mR |= 1u << r; tR = fminf(tR, cr); }
 			}
 			if (!(mL | mR)) goto pop;
 			const int refL = __float_as_int(q1.z), refR = __float_as_int(q3.z);
@@ -417,7 +432,6 @@ RTX_DEV void traverse_packet(const SceneDev &sc, const float4 *__restrict__ pair
 					}
 					best[r].dist = h.dist; best[r].tri = tri; best[r].s = h.s; best[r].t = h.t;
 					cull[r] = h.dist * 1.0001f + abs_margin;
-					limit[r] = fminf(max_distance, cull[r]);
 				}
 			}
 		}
@@ -430,7 +444,7 @@ pop:
 			uint32_t m = 0;
 #pragma unroll
 			for (int r = 0; r < NR; ++r)
-				if (t < limit[r]) m |= 1u << r;
+				if (t < cull[r]) m |= 1u << r;
 			m &= e.y & MBITS;
 			if (m) { cur = (int)e.x; mask = m; break; }
 		}
@@ -919,7 +933,7 @@ k_trace_rays(const SceneDev sc, const RayWork w, Counters *cnt)
 
 struct PtRay {
 	f3 o, d, id;
-	float max_distance, inv_len, abs_margin, cull, limit;
+	float max_distance, inv_len, abs_margin, cull, maxid;
 	HitRec best;
 	int cur, pend, sp;
 	unsigned long long index;
@@ -931,7 +945,7 @@ RTX_DEV int pt_pop(PtRay &r, const uint2 *__restrict__ s_stack, const uint2 *l_s
 	while (r.sp > 0) {
 		--r.sp;
 		const uint2 e = (SMEM_STACK > 0 && r.sp < SMEM_STACK) ? s_stack[r.sp * stride] : l_stack[r.sp - SMEM_STACK];
-		if (__uint_as_float(e.y) < r.limit) return (int)e.x;
+		if (__uint_as_float(e.y) < r.cull) return (int)e.x;
 	}
 	return RTX_PT_DONE;
 }
@@ -995,7 +1009,7 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 							r.inv_len = rsqrtf(fmaxf(r.d.x * r.d.x + r.d.y * r.d.y + r.d.z * r.d.z, 1e-30f));
 							r.abs_margin = 1e-5f * fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fmaxf(fabsf(r.o.z), sc.scene_scale)) * r.inv_len;
 							r.cull = __int_as_float(0x7f800000);
-							r.limit = r.max_distance;
+							r.maxid = fminf(fmaxf(fmaxf(fabsf(r.id.x), fabsf(r.id.y)), fabsf(r.id.z)), 1e30f);   /* see box_slack */
 							r.cur = 0; r.pend = RTX_PT_NONE; r.sp = 0;
 						} else {       /* zero direction component / deep tree: the literal walk, right away */
 							if (COUNT) atomicAdd(&cnt->exact_rays, 1ull);
@@ -1022,8 +1036,9 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 				if (COUNT) visits += 2;
 				const Slab L = slab_interval<false, 4>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r.o, r.id);
 				const Slab R = slab_interval<false, 4>(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, r.o, r.id);
-				const bool hitL = L.tmin <= L.tmax && L.tmin < r.limit && L.tmax > 0.0f;
-				const bool hitR = R.tmin <= R.tmax && R.tmin < r.limit && R.tmax > 0.0f;
+				const float cL = __fmaf_rn(-q1.w, r.maxid, L.tmin), cR = __fmaf_rn(-q3.w, r.maxid, R.tmin);
+				const bool hitL = L.tmin <= L.tmax && L.tmin < r.max_distance && cL < r.cull && L.tmax > 0.0f;
+				const bool hitR = R.tmin <= R.tmax && R.tmin < r.max_distance && cR < r.cull && R.tmax > 0.0f;
 				int next;
 				if (!(hitL || hitR)) {
 					next = pt_pop<SMEM_STACK>(r, s_stack, l_stack, stride);
@@ -1031,7 +1046,7 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 					const int refL = __float_as_int(q1.z), refR = __float_as_int(q3.z);
 					const bool r_first = hitR && (!hitL || R.tmin < L.tmin);
 					if (hitL && hitR) {
-						const uint2 e = make_uint2((uint32_t)(r_first ? refL : refR), __float_as_uint(r_first ? L.tmin : R.tmin));
+						const uint2 e = make_uint2((uint32_t)(r_first ? refL : refR), __float_as_uint(r_first ? cL : cR));
 						if (SMEM_STACK > 0 && r.sp < SMEM_STACK) s_stack[r.sp * stride] = e; else l_stack[r.sp - SMEM_STACK] = e;
 						++r.sp;
 					}
@@ -1063,7 +1078,7 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 				}
 				r.best.dist = h.dist; r.best.tri = tri; r.best.s = h.s; r.best.t = h.t;
 				r.cull = (h.dist * r.inv_len) * 1.0001f + r.abs_margin;
-				r.limit = fminf(r.max_distance, r.cull);
+
 			}
 			r.pend = RTX_PT_NONE;
 			if (r.cur < 0 && r.cur != RTX_PT_DONE) {        /* a second leaf was waiting: park it, move on */
@@ -1478,7 +1493,7 @@ __global__ void k_flatten_nodes(const uint32_t *__restrict__ nodes, const float4
 		for (int v = 0; v < 4; ++v) {
 			float4 *p = pairs + 4 * (size_t)v;
 			p[0] = make_float4((v & 1) ? hi.x : lo.x, (v & 2) ? hi.y : lo.y, lo.z, (v & 1) ? lo.x : hi.x);
-			p[1] = make_float4((v & 2) ? lo.y : hi.y, hi.z, __int_as_float(ref), 0.f);
+			p[1] = make_float4((v & 2) ? lo.y : hi.y, hi.z, __int_as_float(ref), box_slack(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z));
 			p[2] = make_float4(3e38f, 3e38f, 3e38f, 3e38f);
 			p[3] = make_float4(3e38f, 3e38f, __int_as_float(ref), 0.f);
 		}
@@ -1496,7 +1511,7 @@ __global__ void k_flatten_nodes(const uint32_t *__restrict__ nodes, const float4
 		const int ref = clv > leaf_size ? (int)pair_idx[c] : (int)~((first_leaf[c] << 3) | (clv - 1));
 		const float4 lo = ref_aabbs[2 * (size_t)c], hi = ref_aabbs[2 * (size_t)c + 1];
 		a[k] = make_float4(lo.x, lo.y, lo.z, hi.x);
-		b[k] = make_float4(hi.y, hi.z, __int_as_float(ref), 0.f);
+		b[k] = make_float4(hi.y, hi.z, __int_as_float(ref), box_slack(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z));
 	}
 #pragma unroll
 	for (int v = 0; v < 4; ++v) {       /* octant copies: swap lo/hi of x (bit 0) and of y (bit 1) */

@@ -296,6 +296,40 @@ def test_random_ray_batch(po, sibenik_scene):
         assert h.trace_random_rays(1234, 0, 1 << 18)[:2] == a
 
 
+@pytest.mark.parametrize("kernel,leaf", [(0, 1), (1, 1), (0, 2), (1, 4)])
+def test_hit_outside_its_leaf_box_is_not_culled(po, sibenik_scene, kernel, leaf):
+    """Ray 3 664 471 of the seed-1234 batch ties on two coplanar triangles along their shared edge.  The hit on the
+    first lies 8e-7 OUTSIDE that triangle's leaf box (the reference accepts s, t down to -1e-5), and with
+    d.x = -0.00136 the ray enters the box 6e-4 later than it hits the triangle: distance culling has to allow for
+    that (box_slack), or the second triangle wins the tie.  Found by comparing the two arbitrary-ray kernels'
+    checksums over 2^28 rays."""
+    host = require_gpu()
+    lo, hi = sibenik_scene.root_box()
+    o, d = po.gen_random_rays(1234, 3664448, 32, lo, hi)
+    ref = po.trace_rays(sibenik_scene, o, d, 100000.0)
+    assert ref.face_id[23] == 180396
+    rt = host.RayTracer(host.Options(width=32, height=32, nSuperSamples=1))
+    with host.CudaHost(rt) as h:
+        h.set_tunable(host.TUNE_INCOHERENT_KERNEL, kernel)
+        h.set_tunable(host.TUNE_LEAF_SIZE, leaf)
+        h.upload_scene(sibenik_scene)
+        fid, dist = h.trace_rays(o, d)
+        assert np.array_equal(fid, ref.face_id) and np.array_equal(dist, ref.distance)
+        fid, dist = h.trace_rays(o[23:24], d[23:24])
+        assert fid[0] == 180396
+
+
+def test_arbitrary_ray_kernels_agree_on_a_large_batch(sibenik_scene):
+    """2^26 generated rays: the refill kernel and the plain while-while kernel give the same hit count and id sum."""
+    host = require_gpu()
+    rt = host.RayTracer(host.Options(width=32, height=32, nSuperSamples=1))
+    with host.CudaHost(rt) as h:
+        h.upload_scene(sibenik_scene)
+        a = h.trace_random_rays(1234, 0, 1 << 26)[:2]
+        h.set_tunable(host.TUNE_INCOHERENT_KERNEL, 0)
+        assert h.trace_random_rays(1234, 0, 1 << 26)[:2] == a
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_tile_partition_equals_single_image(po, soup_scene, world):
     """The multi-GPU data path emulated on one GPU: `world` contexts render their interleaved tiles into
