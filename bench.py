@@ -246,10 +246,14 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = []
     barrier()
+    rendezvous = torch.zeros(1, dtype=torch.int32, device=dev)
     for k in range(args.steps):
         flush.zero_()                                   # L2 flush between timed iterations (not timed)
         if world > 1:
-            dist.barrier()
+            # per-step rendezvous ON THE DEVICE: a one-element all-reduce the launching stream waits for.  All ranks
+            # leave it within microseconds of each other, and the host runs ahead enqueueing the frame, so the step's
+            # events do not measure the wake-up jitter of N host processes after a host-side barrier.
+            dist.all_reduce(rendezvous)
         ev[k][0].record()
         r.render_frame()
         ev[k][1].record()

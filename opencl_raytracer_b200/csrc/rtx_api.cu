@@ -381,6 +381,14 @@ cudaError_t launch_rays(rtx_ctx *c, const RayWork &w, cudaStream_t st)
 	return cnt ? launch_rays_t<false, true>(c, w, st) : launch_rays_t<false, false>(c, w, st);
 }
 
+void launch_resize_u8(const float *src, uint32_t W, uint32_t w, uint32_t h, uint32_t n, unsigned char *out, dim3 grid, dim3 block, cudaStream_t st)
+{
+	const bool aligned = W == w * n && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+	if (n == 4 && aligned) k_resize_u8_vec<4><<<grid, block, 0, st>>>(src, W, w, h, out);
+	else if (n == 2 && aligned) k_resize_u8_vec<2><<<grid, block, 0, st>>>(src, W, w, h, out);
+	else k_resize_u8<<<grid, block, 0, st>>>(src, W, w, h, n, out);
+}
+
 int finish_stats(rtx_ctx *c)
 {
 	if (c->ev_pending) {
@@ -983,7 +991,7 @@ int rtx_resize_u8_async(rtx_ctx *c, void *d_tiles_u8, size_t count, void *stream
 		CU(c, c->d_u8.alloc((size_t)w * h));
 		const float *src = c->ext_image ? c->ext_image : c->d_image.as<float>();
 		const dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-		k_resize_u8<<<grid, block, 0, st>>>(src, c->W, w, h, n, c->d_u8.as<unsigned char>());
+		launch_resize_u8(src, c->W, w, h, n, c->d_u8.as<unsigned char>(), grid, block, st);
 		CU(c, cudaGetLastError());
 		c->u8_valid = true;
 		return RTX_OK;
@@ -1031,7 +1039,7 @@ int rtx_download_u8(rtx_ctx *c, unsigned char *image)
 	CU(c, cudaSetDevice(c->device));
 	CU(c, c->d_u8.alloc((size_t)w * h));
 	const dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-	k_resize_u8<<<grid, block, 0, c->stream>>>(src, c->W, w, h, n, c->d_u8.as<unsigned char>());
+	launch_resize_u8(src, c->W, w, h, n, c->d_u8.as<unsigned char>(), grid, block, c->stream);
 	CU(c, cudaGetLastError());
 	CU(c, cudaMemcpyAsync(image, c->d_u8.p, (size_t)w * h, cudaMemcpyDeviceToHost, c->stream));
 	CU(c, cudaStreamSynchronize(c->stream));
