@@ -94,3 +94,14 @@ def ao_golden():
 
 
 AO_CASES = ("uniform3", "random3", "random1_far", "uniform2_a10_60", "uniform2_d07")
+
+
+@pytest.fixture(scope="session")
+def sah_golden():
+    return load_golden("soup_sah.npz")
+
+
+@pytest.fixture(scope="session")
+def sah_scene(scene_mod, sah_golden):
+    g = sah_golden
+    return scene_mod.Scene(g["t_faces"], g["t_nodes"], g["t_aabbs"], g["t_vertices"], g["t_normals"])

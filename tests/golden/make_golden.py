@@ -13,6 +13,8 @@ restatement or the CUDA path.  Outputs (small, committed):
   soup_rays.npz       4096 arbitrary rays (incl. axis-parallel ones) and their hits
   quad_33x17.npz      two big triangles sharing a diagonal, odd image size
   scenes.json         sha256 digests of the reference builder's arrays + bunny known answers
+  soup_sah.npz        the soup's tree from the reference's SAH builder (`-r sah`, bvh.cc:178-236) as upload arrays +
+                      its render; `python tests/golden/make_golden.py sah` writes only this file
   soup_ao.npz         the soup with ambient occlusion (uniform rings 3, random 3, random 1 with a longer reach);
                       `python tests/golden/make_golden.py ao` writes only this file
 """
@@ -64,10 +66,35 @@ def make_ao():
     print("soup_ao.npz written")
 
 
+def make_sah():
+    """A tree of different topology for the same triangles: the reference's O(n^2) SAH builder (chatty on stdout)."""
+    v, f = scenes.random_soup(300, seed=11)
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        r = po.ref_scene_from_mesh(v, f, sah=True)
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+    sc = Scene(r.faces, r.nodes, r.aabbs, r.vertices, r.normals, r.triangles, r.orig_faces)
+    out = render_case(sc, 32, 24, 4)
+    ao = po.Ao.make(method=0, samples=2, max_distance=0.7)
+    tw, th = po.ref_total_dims(32, 24, 4)
+    img_ao = po.ref_render_ao(sc, tw, th, ao, po.ref_focal_roundtrip(1.0))
+    np.savez_compressed(os.path.join(OUT, "soup_sah.npz"), t_faces=sc.faces, t_nodes=sc.nodes, t_aabbs=sc.aabbs,
+                        t_vertices=sc.vertices, t_normals=sc.normals, image_ao_uniform2_d07=img_ao, **out)
+    print("soup_sah.npz written (%d nodes)" % sc.nodes.size)
+
+
 def main():
     assert po.ref() is not None, "oracle/_ref/libref_oracle.so missing: run make -C oracle"
     if sys.argv[1:] == ["ao"]:
         return make_ao()
+    if sys.argv[1:] == ["sah"]:
+        return make_sah()
     digests = {}
 
     v, f = scenes.random_soup(300, seed=11)
@@ -123,6 +150,7 @@ def main():
                        focal_roundtrip={str(x): po.ref_focal_roundtrip(x) for x in (1.0, 1.2345678, 0.5, 3.3333333, 0.001, 123456.789)}),
                   fh, indent=1, sort_keys=True)
     make_ao()
+    make_sah()
     print("golden vectors written to", OUT)
 
 

@@ -165,3 +165,18 @@ def test_ambient_occlusion_port_matches_reference_library_live(po, sibenik_scene
         r = po.render(sibenik_scene, W, H, 1.0, True, ao=ao)
         img = po.ref_render_ao(sibenik_scene, W, H, ao)
         assert np.array_equal(_bits(r.image), _bits(img))
+
+
+def test_port_on_the_reference_sah_tree(po, sah_scene, sah_golden, soup_scene):
+    """The path consumes whatever tree bvh.cc builds: `-r sah` (bvh.cc:178-236) gives another topology for the same
+    triangles.  Arrays and renders come from the reference builder / kernel text (tests/golden/make_golden.py sah)."""
+    g = sah_golden
+    assert sah_scene.nodes.size == soup_scene.nodes.size and not np.array_equal(sah_scene.nodes, soup_scene.nodes)
+    r = po.render(sah_scene, 64, 48, 1.0, True)
+    assert np.array_equal(r.face_id, g["face_id"]) and np.array_equal(_bits(r.distance), _bits(g["distance"]))
+    assert np.array_equal(_bits(r.image), _bits(g["image"]))
+    ao = po.Ao.make(method=0, samples=2, max_distance=0.7)
+    assert np.array_equal(_bits(po.render(sah_scene, 64, 48, 1.0, True, ao=ao).image), _bits(g["image_ao_uniform2_d07"]))
+    # same triangles, other leaf order: same picture wherever no two triangles tie
+    plain = po.render(soup_scene, 64, 48, 1.0, True)
+    assert (r.distance == plain.distance).mean() > 0.999

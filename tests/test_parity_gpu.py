@@ -60,6 +60,32 @@ def test_soup_matches_reference_golden(po, soup_scene, soup_golden, kernel, leaf
         assert np.array_equal(h.download_u8(), g["u8"])
 
 
+@pytest.mark.parametrize("kernel,leaf,frustum", [(1, 1, 0), (0, 1, 0), (0, 1, 1), (0, 4, -1)])
+def test_reference_sah_tree(po, sah_scene, sah_golden, kernel, leaf, frustum):
+    """A tree from the reference's SAH builder (`render -r sah`), uploaded as the arrays bvh.cc produced."""
+    host = require_gpu()
+    g = sah_golden
+    rt = host.RayTracer(host.Options(width=int(g["width"]), height=int(g["height"]), nSuperSamples=int(g["nss"])))
+    with host.CudaHost(rt) as h:
+        h.set_tunable(host.TUNE_KERNEL, kernel)
+        h.set_tunable(host.TUNE_LEAF_SIZE, leaf)
+        h.set_tunable(host.TUNE_FRUSTUM, frustum)
+        h.set_tunable(host.TUNE_RECORD_HITS, 1)
+        h.upload_scene(sah_scene)
+        h()
+        fid, dist = h.download_hits()
+        assert np.array_equal(fid, g["face_id"]) and np.array_equal(dist, g["distance"])
+        assert np.array_equal(h.download(), g["image"])
+        assert np.array_equal(h.download_u8(), g["u8"])
+    rt = host.RayTracer(host.Options(width=int(g["width"]), height=int(g["height"]), nSuperSamples=int(g["nss"]), enableAO=True,
+                                     aoNumSamples=2, aoMaxDistance=0.7))
+    with host.CudaHost(rt) as h:
+        h.set_tunable(host.TUNE_LEAF_SIZE, leaf)
+        h.upload_scene(sah_scene)
+        h()
+        assert np.array_equal(h.download(), g["image_ao_uniform2_d07"])
+
+
 def test_bunny_c1(po, bunny_scene, golden_meta):
     """Config C1: bunny.off, render -a 0 defaults (600x600, s=4 -> 1 440 000 rays)."""
     host = require_gpu()
