@@ -323,6 +323,9 @@ def main():
         np_arrs = [a.numpy() for a in arrs]
         h2d = int(sum(a.numel() * a.element_size() for a in arrs))
         out_f = torch.empty((th, tw), dtype=torch.float32).pin_memory().numpy() if rank == 0 else None
+        # N > 1: download(float*) needs the float tiles gathered, download_u8 the byte tiles -- one renderer per payload
+        r_float = r if (world == 1 or args.gather == "float") else multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather="float")
+        r_u8 = r if (world == 1 or args.gather == "u8") else multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather="u8")
         hr = r.host
 
         phase = {}
@@ -333,15 +336,15 @@ def main():
             phase[name] = phase.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
             return out
 
-        def render_sync():
-            r.render_frame()
+        def render_sync(rr):
+            rr.render_frame()
             torch.cuda.synchronize(dev)
 
         def frame_float():
-            timed("upload", lambda: hr.upload(*np_arrs))
-            timed("render", render_sync)
+            timed("upload", lambda: r_float.host.upload(*np_arrs))
+            timed("render", lambda: render_sync(r_float))
             if rank == 0:
-                timed("download", lambda: hr.download(out_f))
+                timed("download", lambda: r_float.host.download(out_f))
 
         def frame_pipelined():
             # N = 1: upload, then trace + download as ONE call (rtx_render_download): bands of tile rows, the
@@ -350,10 +353,10 @@ def main():
             timed("render+download", lambda: hr.render_download(out_f))
 
         def frame_u8():
-            timed("upload", lambda: hr.upload(*np_arrs))
-            timed("render", render_sync)
+            timed("upload", lambda: r_u8.host.upload(*np_arrs))
+            timed("render", lambda: render_sync(r_u8))
             if rank == 0:
-                timed("download", lambda: hr.download_u8())
+                timed("download", lambda: r_u8.host.download_u8())
 
         res, phases = [], []
         fns = (frame_float, frame_u8) + ((frame_pipelined,) if world == 1 else ())
@@ -389,6 +392,9 @@ def main():
         e2e_u8 = {"value": res[1], "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": width * height,
                   "calls": "rtx_upload + rtx_render(+gather) + rtx_download_u8 (device resize, ray_tracer.cc:3-15 order)",
                   "phase_ms": phases[1]}
+        for rr in (r_float, r_u8):
+            if rr is not r:
+                rr.close()
 
     # ---------------- extras (N = 1): same frame, other code paths, kernel time only ----------------
     extras = None
