@@ -80,8 +80,7 @@ struct rtx_ctx {
 	SceneDev sc{};
 	DevBuf d_pairs, d_tris, d_leafbox, d_tnormals, d_ref_nodes, d_ref_aabbs;
 	DevBuf t_faces, t_verts, t_vnormals, t_scan;   /* upload staging, kept between uploads */
-	std::vector<uint32_t> h_scan;
-	std::vector<size_t> h_ends;
+	TreeResult h_tree{};         /* result words of the device-side tree check (k_tree_*) */
 	f3 bbmin{}, bbmax{};
 	uint32_t tree_depth = 0;
 	/* image */
@@ -627,59 +626,50 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	/* the copies above are in flight while the host validates and scans */
 	const bool device_flatten = c->flatten_on_device && c->top_smem == 0;
 	std::string why;
-	size_t num_pairs = 0;
+	size_t num_pairs = 0, pair_stride = 0;
 	uint32_t depth = 0, top_pairs = 0;
 	if (device_flatten) {
-		/* ONE host pass over the nodes: the invariants of SURVEY 3.3 (validate_tree), the two prefix counts
-		 * k_flatten_nodes needs, and the depth of the flattened tree. */
+		/* The tree's invariants, the two prefix counts k_flatten_nodes needs and the depth of the
+		 * flattened tree are all computed on the device from the raw arrays (k_tree_*): no host pass over the nodes. */
 		if (nnodes == 0 || nodes[0] != nnodes || (nnodes & 1) == 0 || leaves_of((uint32_t)nnodes) != ntris)
 			return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: node count must be 2*triangles-1 and nodes[0] must equal it");
-		std::vector<uint32_t> &scan = c->h_scan;
-		scan.resize(2 * nnodes);
-		uint32_t *first_leaf = scan.data(), *pair_idx = scan.data() + nnodes;
-		std::vector<size_t> &ends = c->h_ends;          /* pre-order ends of the open internal nodes */
-		ends.clear();
-		uint32_t nl = 0, np = 0;
-		const uint32_t K = (uint32_t)c->leaf_size;
-		for (size_t i = 0; i < nnodes; ++i) {
-			while (!ends.empty() && ends.back() == i) ends.pop_back();
-			first_leaf[i] = nl;
-			pair_idx[i] = np;
-			const size_t size = nodes[i];
-			if (size == 1) { ++nl; continue; }
-			if ((size & 1) == 0 || i + size > nnodes) return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: subtree size out of range at node " + std::to_string(i));
-			const size_t l = nodes[i + 1];
-			if ((l & 1) == 0 || l + 2 > size || nodes[i + 1 + l] != size - 1 - l)
-				return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: children do not tile node " + std::to_string(i));
-			if (leaves_of((uint32_t)size) > K || i == 0) {
-				++np;
-				ends.push_back(i + size);
-				if (ends.size() > depth) depth = (uint32_t)ends.size();
-			}
+		const uint32_t K = (uint32_t)c->leaf_size, n = (uint32_t)nnodes;
+		pair_stride = ntris > 1 ? ntris - 1 : 1;                       /* internal nodes of a full binary tree: the bound for any K */
+		const uint32_t per_block = RTX_SCAN_BLOCK * RTX_SCAN_ITEMS, nblocks = (n + per_block - 1) / per_block;
+		CUU(c->t_scan.alloc(((size_t)3 * n + (size_t)3 * nblocks + 4) * 4));
+		uint32_t *first_leaf = c->t_scan.as<uint32_t>(), *pair_idx = first_leaf + n;
+		int *delta = reinterpret_cast<int *>(pair_idx + n), *partials = delta + n;
+		TreeResult *res = reinterpret_cast<TreeResult *>(partials + (size_t)3 * nblocks);
+		CUU(c->d_pairs.alloc(4 * pair_stride * 64));
+		c->h_tree = TreeResult{ 0xffffffffu, 0u, n == 1 ? 1u : 0u, n == 1 ? 1u : 0u };
+		CUU(cudaMemcpyAsync(res, &c->h_tree, sizeof(TreeResult), cudaMemcpyHostToDevice, st));
+		if (n > 1) {
+			CUU(cudaMemsetAsync(delta, 0, (size_t)n * 4, st));
+			k_tree_check<<<(n + 255) / 256, 256, 0, st>>>(c->d_ref_nodes.as<uint32_t>(), n, K, delta, res);
+			k_tree_partials<<<nblocks, RTX_SCAN_BLOCK, 0, st>>>(c->d_ref_nodes.as<uint32_t>(), delta, n, K, partials);
+			k_tree_spine<<<1, 96, 0, st>>>(partials, nblocks, res);
+			k_tree_scan<<<nblocks, RTX_SCAN_BLOCK, 0, st>>>(c->d_ref_nodes.as<uint32_t>(), delta, n, K, partials, first_leaf, pair_idx, res);
+		} else {
+			CUU(cudaMemsetAsync(first_leaf, 0, 2 * sizeof(uint32_t), st));
 		}
-		if (nnodes == 1) { np = 1; depth = 1; }
-		num_pairs = np;
-	} else if (!validate_tree(nodes, nnodes, ntris, why)) {
-		return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: " + why);
-	}
-	{
+		k_flatten_nodes<<<(unsigned)((nnodes + 255) / 256), 256, 0, st>>>(
+			c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>(), first_leaf, pair_idx,
+			c->t_faces.as<uint32_t>(), c->t_verts.as<float4>(), c->t_vnormals.as<float4>(), n, (uint32_t)pair_stride, K,
+			c->d_pairs.as<float4>(), c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>(), (uint32_t)nverts, res);
+		CUU(cudaGetLastError());
+		CUU(cudaMemcpyAsync(&c->h_tree, res, sizeof(TreeResult), cudaMemcpyDeviceToHost, st));
+		CUU(cudaStreamSynchronize(st));
+		if (c->h_tree.bad_node != 0xffffffffu)
+			return fail(c, RTX_ERR_ARG, "malformed BVH: subtree sizes do not form a pre-order binary tree at node " + std::to_string(c->h_tree.bad_node));
+		if (c->h_tree.bad_face) return fail(c, RTX_ERR_ARG, "face index out of range");
+		num_pairs = c->h_tree.num_pairs;
+		depth = c->h_tree.depth;
+	} else {
+		/* host flatten (needed for the breadth-first prefix that RTX_TUNE_TOP_SMEM stages in shared memory) */
+		if (!validate_tree(nodes, nnodes, ntris, why)) return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: " + why);
 		uint32_t bad = 0;                          /* branch-free range check of the vertex indices */
 		for (size_t i = 0; i < nfaceidx; ++i) bad |= (uint32_t)(faces[i] >= nverts);
 		if (bad) return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "face index out of range");
-	}
-	if (device_flatten) {
-		const uint32_t K = (uint32_t)c->leaf_size;
-		std::vector<uint32_t> &scan = c->h_scan;
-		CUU(c->t_scan.alloc(2 * nnodes * 4));
-		CUU(c->d_pairs.alloc(4 * num_pairs * 64));
-		CUU(cudaMemcpyAsync(c->t_scan.p, scan.data(), 2 * nnodes * 4, cudaMemcpyHostToDevice, st));
-		k_flatten_nodes<<<(unsigned)((nnodes + 255) / 256), 256, 0, st>>>(
-			c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>(), c->t_scan.as<uint32_t>(), c->t_scan.as<uint32_t>() + nnodes,
-			c->t_faces.as<uint32_t>(), c->t_verts.as<float4>(), c->t_vnormals.as<float4>(), (uint32_t)nnodes, (uint32_t)num_pairs, K,
-			c->d_pairs.as<float4>(), c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>());
-		CUU(cudaGetLastError());
-	} else {
-		/* host flatten (needed for the breadth-first prefix that RTX_TUNE_TOP_SMEM stages in shared memory) */
 		Flat flat;
 		flatten(nodes, aabbs16, nnodes, c->leaf_size, c->top_smem > 0 ? (uint32_t)c->top_smem : 0u, flat);
 		const size_t pair_vecs = flat.pairs.size();
@@ -694,7 +684,7 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 				dst[i + 1] = b;
 			}
 		}
-		num_pairs = pair_vecs / 4;
+		num_pairs = pair_stride = pair_vecs / 4;
 		depth = flat.depth;
 		top_pairs = flat.top_pairs;
 		CUU(c->t_scan.alloc(ntris * 4));
@@ -716,7 +706,7 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	c->sc.tnormals = c->d_tnormals.as<float4>();
 	c->sc.ref_nodes = c->d_ref_nodes.as<uint32_t>();
 	c->sc.ref_aabbs = c->d_ref_aabbs.as<float4>();
-	c->sc.num_pairs = (uint32_t)num_pairs;
+	c->sc.num_pairs = (uint32_t)pair_stride;            /* distance between the octant copies */
 	c->sc.top_pairs = c->top_smem > 0 ? top_pairs : 0;
 	c->sc.num_tris = (uint32_t)ntris;
 	c->sc.verify_leafbox = c->leaf_size > 1 ? 1u : 0u;
@@ -727,7 +717,7 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	c->sc.scene_scale = scale;
 	c->tree_depth = depth;
 	c->stats.tree_depth = depth;
-	c->stats.num_pairs = c->sc.num_pairs;
+	c->stats.num_pairs = (uint32_t)num_pairs;
 	c->uploaded = true;
 	c->rendered = false;
 	return RTX_OK;

@@ -1478,6 +1478,143 @@ __global__ void k_deinterleave(const float *__restrict__ gathered, uint32_t worl
 
 /* ------------------- device-side pieces of the flatten ------------------- */
 
+/* --------------------------------------------------------------------------
+ * Upload, device side: the invariants of the reference's pre-order tree (bvh.cc:98-162) and the two
+ * prefix counts the flatten kernel needs, computed from the raw `nodes` array on the device -- no host pass
+ * over the tree (20 M nodes at C4).
+ *   first_leaf[i]  leaves before node i in pre-order  = exclusive sum of [nodes[j] == 1]
+ *   pair_idx[i]    flattened internal nodes before i  = exclusive sum of [node j becomes a pair]
+ *   depth          1 + most "pair" ancestors of any pair: +1 at j+1 and -1 at j+nodes[j] for every pair j,
+ *                  summed in pre-order (k_tree_check scatters the +-1, the scan integrates them)
+ * Three kernels: per-block partial sums, one block over the partials, per-block scan + write.
+ * ------------------------------------------------------------------------ */
+struct TreeResult {
+	unsigned int bad_node;      /* smallest index that breaks an invariant, or 0xffffffff */
+	unsigned int bad_face;      /* 1 if a face index is out of range */
+	unsigned int num_pairs;
+	unsigned int depth;
+};
+
+#define RTX_SCAN_ITEMS 16       /* nodes per thread */
+#define RTX_SCAN_BLOCK 256
+
+RTX_DEV bool tree_is_pair(uint32_t size, uint32_t i, uint32_t leaf_size) { return size > 1 && (((size + 1) >> 1) > leaf_size || i == 0); }
+
+__global__ void k_tree_check(const uint32_t *__restrict__ nodes, uint32_t n, uint32_t leaf_size, int *__restrict__ delta, TreeResult *res)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t size = nodes[i];
+	if (size == 1) return;
+	bool ok = (size & 1u) != 0 && size >= 3 && (uint64_t)i + size <= n;
+	if (ok) {
+		const uint32_t l = nodes[i + 1];
+		ok = (l & 1u) != 0 && l + 2 <= size && nodes[i + 1 + l] == size - 1 - l;
+	}
+	if (!ok) { atomicMin(&res->bad_node, i); return; }
+	if (tree_is_pair(size, i, leaf_size)) {
+		atomicAdd(delta + i + 1, 1);
+		if (i + size < n) atomicAdd(delta + i + size, -1);
+	}
+}
+
+/* block sums of the three scanned quantities -> partials[3][nblocks] */
+__global__ void __launch_bounds__(RTX_SCAN_BLOCK)
+k_tree_partials(const uint32_t *__restrict__ nodes, const int *__restrict__ delta, uint32_t n, uint32_t leaf_size, int *__restrict__ partials)
+{
+	__shared__ int s[3][RTX_SCAN_BLOCK / 32];
+	const uint32_t base = (blockIdx.x * RTX_SCAN_BLOCK + threadIdx.x) * RTX_SCAN_ITEMS;
+	int a = 0, b = 0, c = 0;
+	for (uint32_t k = 0; k < RTX_SCAN_ITEMS; ++k) {
+		const uint32_t i = base + k;
+		if (i < n) {
+			const uint32_t size = nodes[i];
+			a += size == 1;
+			b += tree_is_pair(size, i, leaf_size);
+			c += delta[i];
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		a += __shfl_xor_sync(0xffffffffu, a, o);
+		b += __shfl_xor_sync(0xffffffffu, b, o);
+		c += __shfl_xor_sync(0xffffffffu, c, o);
+	}
+	if ((threadIdx.x & 31) == 0) { s[0][threadIdx.x >> 5] = a; s[1][threadIdx.x >> 5] = b; s[2][threadIdx.x >> 5] = c; }
+	__syncthreads();
+	if (threadIdx.x < 3) {
+		int t = 0;
+		for (int w = 0; w < RTX_SCAN_BLOCK / 32; ++w) t += s[threadIdx.x][w];
+		partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = t;
+	}
+}
+
+/* exclusive scan of each row of partials, in place; one block, one warp per row */
+__global__ void k_tree_spine(int *__restrict__ partials, uint32_t nblocks, TreeResult *res)
+{
+	const uint32_t row = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	if (row >= 3) return;
+	int *p = partials + (size_t)row * nblocks;
+	int carry = 0;
+	for (uint32_t base = 0; base < nblocks; base += 32) {
+		const uint32_t i = base + lane;
+		const int v = i < nblocks ? p[i] : 0;
+		int x = v;
+		for (int o = 1; o < 32; o <<= 1) {
+			const int y = __shfl_up_sync(0xffffffffu, x, o);
+			if ((int)lane >= o) x += y;
+		}
+		if (i < nblocks) p[i] = carry + x - v;
+		carry += __shfl_sync(0xffffffffu, x, 31);
+	}
+	if (row == 1 && lane == 0) res->num_pairs = (unsigned int)carry;
+}
+
+__global__ void __launch_bounds__(RTX_SCAN_BLOCK)
+k_tree_scan(const uint32_t *__restrict__ nodes, const int *__restrict__ delta, uint32_t n, uint32_t leaf_size,
+            const int *__restrict__ partials, uint32_t *__restrict__ first_leaf, uint32_t *__restrict__ pair_idx, TreeResult *res)
+{
+	__shared__ int s[3][RTX_SCAN_BLOCK / 32];
+	const uint32_t base = (blockIdx.x * RTX_SCAN_BLOCK + threadIdx.x) * RTX_SCAN_ITEMS;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	int a = 0, b = 0, c = 0;
+	for (uint32_t k = 0; k < RTX_SCAN_ITEMS; ++k) {
+		const uint32_t i = base + k;
+		if (i < n) {
+			const uint32_t size = nodes[i];
+			a += size == 1;
+			b += tree_is_pair(size, i, leaf_size);
+			c += delta[i];
+		}
+	}
+	/* exclusive scan of the thread sums over the block */
+	int xa = a, xb = b, xc = c;
+	for (int o = 1; o < 32; o <<= 1) {
+		const int ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o), yc = __shfl_up_sync(0xffffffffu, xc, o);
+		if ((int)lane >= o) { xa += ya; xb += yb; xc += yc; }
+	}
+	if (lane == 31) { s[0][warp] = xa; s[1][warp] = xb; s[2][warp] = xc; }
+	__syncthreads();
+	int oa = partials[blockIdx.x], ob = partials[(size_t)gridDim.x + blockIdx.x], oc = partials[2 * (size_t)gridDim.x + blockIdx.x];
+	for (uint32_t w = 0; w < warp; ++w) { oa += s[0][w]; ob += s[1][w]; oc += s[2][w]; }
+	oa += xa - a; ob += xb - b; oc += xc - c;
+	int deepest = 0;
+	for (uint32_t k = 0; k < RTX_SCAN_ITEMS; ++k) {
+		const uint32_t i = base + k;
+		if (i < n) {
+			const uint32_t size = nodes[i];
+			first_leaf[i] = (uint32_t)oa;
+			pair_idx[i] = (uint32_t)ob;
+			oc += delta[i];                       /* pair ancestors of node i */
+			const bool pair = tree_is_pair(size, i, leaf_size);
+			if (pair && oc + 1 > deepest) deepest = oc + 1;
+			oa += size == 1;
+			ob += pair;
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) deepest = max(deepest, __shfl_xor_sync(0xffffffffu, deepest, o));
+	if (lane == 0 && deepest > 0) atomicMax(&res->depth, (unsigned int)deepest);
+}
+
 /* The whole flatten in one pass over the reference's pre-order nodes (rtx_upload's default path).
  * A node is an internal node of the flattened tree iff its subtree holds more than `leaf_size` triangles
  * (or it is the root); in pre-order its pair index is the number of such nodes before it, and the first
@@ -1489,14 +1626,19 @@ __global__ void k_flatten_nodes(const uint32_t *__restrict__ nodes, const float4
                                 const uint32_t *__restrict__ faces, const float4 *__restrict__ verts,
                                 const float4 *__restrict__ vnormals, uint32_t nnodes, uint32_t num_pairs, uint32_t leaf_size,
                                 float4 *__restrict__ pairs, float4 *__restrict__ tris, float4 *__restrict__ leafbox,
-                                float4 *__restrict__ tnormals)
+                                float4 *__restrict__ tnormals, uint32_t nverts, TreeResult *res)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nnodes) return;
+	if (res && res->bad_node != 0xffffffffu) return;          /* malformed tree (k_tree_check): nothing below is safe */
 	const uint32_t size = nodes[i];
 	if (size == 1) {
 		const uint32_t t = first_leaf[i];
-		const uint32_t i0 = faces[3 * (size_t)t], i1 = faces[3 * (size_t)t + 1], i2 = faces[3 * (size_t)t + 2];
+		uint32_t i0 = faces[3 * (size_t)t], i1 = faces[3 * (size_t)t + 1], i2 = faces[3 * (size_t)t + 2];
+		if (i0 >= nverts || i1 >= nverts || i2 >= nverts) {    /* reported by rtx_upload; keep the reads in range */
+			if (res) res->bad_face = 1u;
+			i0 = i1 = i2 = 0;
+		}
 		const float4 A = verts[i0], B = verts[i1], C = verts[i2];
 		const f3 a = make_f3(A.x, A.y, A.z);
 		const f3 u = sub3(make_f3(B.x, B.y, B.z), a);                 /* :68 */

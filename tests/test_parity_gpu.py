@@ -401,6 +401,29 @@ def test_tile_partition_equals_single_image(po, soup_scene, world):
             c.close()
 
 
+@pytest.mark.parametrize("leaf", [1, 2, 4, 8])
+def test_device_tree_scan_equals_host_flatten(po, soup_scene, sah_scene, sibenik_scene, leaf):
+    """rtx_upload validates the tree and computes the flatten's prefix counts and depth on the device (k_tree_*);
+    the host flatten (RTX_TUNE_FLATTEN_ON_DEVICE = 0) must agree on pair count and depth, and both render alike."""
+    host = require_gpu()
+    rt = host.RayTracer(host.Options(width=96, height=64, nSuperSamples=1))
+    for sc in (soup_scene, sah_scene, sibenik_scene):
+        out = []
+        for on_device in (1, 0):
+            with host.CudaHost(rt) as h:
+                h.set_tunable(host.TUNE_FLATTEN_ON_DEVICE, on_device)
+                h.set_tunable(host.TUNE_LEAF_SIZE, leaf)
+                h.set_tunable(host.TUNE_RECORD_HITS, 1)
+                h.upload_scene(sc)
+                h()
+                st = h.stats()
+                out.append((st["num_pairs"], st["tree_depth"], h.download(), h.download_hits()[0]))
+        assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+        assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][3], out[1][3])
+        if leaf == 1:
+            assert out[0][0] == sc.num_triangles - 1
+
+
 def test_error_behaviour(soup_scene):
     host = require_gpu()
     rt = host.RayTracer(host.Options(width=16, height=16, nSuperSamples=1))
@@ -419,6 +442,22 @@ def test_error_behaviour(soup_scene):
         with pytest.raises(host.RtxError) as e:
             h.upload(soup_scene.faces[:-3], soup_scene.nodes, soup_scene.aabbs, soup_scene.vertices, soup_scene.normals)
         assert e.value.code == host.ERR_ARG
+        bad_faces = soup_scene.faces.copy()
+        bad_faces[100] = soup_scene.vertices.shape[0]
+        for on_device in (1, 0):
+            h.set_tunable(host.TUNE_FLATTEN_ON_DEVICE, on_device)
+            with pytest.raises(host.RtxError) as e:
+                h.upload(bad_faces, soup_scene.nodes, soup_scene.aabbs, soup_scene.vertices, soup_scene.normals)
+            assert e.value.code == host.ERR_ARG and "face index" in str(e.value)
+            for k, delta in ((1, 2), (5, 1), (0, -2), (soup_scene.nodes.size - 2, 2)):
+                bad_nodes = soup_scene.nodes.copy()
+                bad_nodes[k] = np.uint32(int(bad_nodes[k]) + delta)
+                with pytest.raises(host.RtxError) as e:
+                    h.upload(soup_scene.faces, bad_nodes, soup_scene.aabbs, soup_scene.vertices, soup_scene.normals)
+                assert e.value.code == host.ERR_ARG and "BVH" in str(e.value)
+            with pytest.raises(host.RtxError):
+                h()                                                # a failed upload leaves nothing to render
+        h.set_tunable(host.TUNE_FLATTEN_ON_DEVICE, 1)
         h.upload_scene(soup_scene)
         assert h() is True
     with pytest.raises(host.RtxError) as e:
