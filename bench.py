@@ -323,6 +323,7 @@ def main():
         np_arrs = [a.numpy() for a in arrs]
         h2d = int(sum(a.numel() * a.element_size() for a in arrs))
         out_f = torch.empty((th, tw), dtype=torch.float32).pin_memory().numpy() if rank == 0 else None
+        out_b = torch.empty((height, width), dtype=torch.uint8).pin_memory().numpy() if rank == 0 else None
         # N > 1: download(float*) needs the float tiles gathered, download_u8 the byte tiles -- one renderer per payload
         r_float = r if (world == 1 or args.gather == "float") else multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather="float")
         r_u8 = r if (world == 1 or args.gather == "u8") else multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather="u8")
@@ -356,7 +357,7 @@ def main():
             timed("upload", lambda: r_u8.host.upload(*np_arrs))
             timed("render", lambda: render_sync(r_u8))
             if rank == 0:
-                timed("download", lambda: r_u8.host.download_u8())
+                timed("download", lambda: r_u8.host.download_u8(out_b))
 
         res, phases = [], []
         fns = (frame_float, frame_u8) + ((frame_pipelined,) if world == 1 else ())

@@ -310,8 +310,10 @@ class CudaHost:
         self._ck(self._lib.rtx_download_hits(self._ctx, fid.ctypes.data, dist.ctypes.data))
         return fid, dist
 
-    def download_u8(self) -> np.ndarray:
-        out = np.empty((self.rt.options.height, self.rt.options.width), np.uint8)
+    def download_u8(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.rt.options.height, self.rt.options.width), np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == self.rt.options.width * self.rt.options.height
         self._ck(self._lib.rtx_download_u8(self._ctx, out.ctypes.data))
         return out
 
