@@ -443,7 +443,7 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": peak_src,
                     "kernel": "k_render_packet<MODE 1> (candidate-list kernel; ~96 % of the traversal time, with k_frustum_collect* "
-                              "and the overflow launch inside the same event pair; profiles/r1_c3_step6_launches.csv)",
+                              "and the overflow launch inside the same event pair; profiles/r1_c3_final_launches.csv)",
                     "kernel_ms": kernel_ms_mean,
                     "algorithmic_bytes_per_ray": B, "V": V, "T": T, "h": hfrac,
                     "note": "SURVEY 8d algorithmic bytes follow the reference's exhaustive walk (V box tests, T triangle tests per ray). "
@@ -456,7 +456,7 @@ def main():
                            "peak_source": "rtx_probe_bandwidth: ld.cg float4 sweep of a 32 MiB buffer, this run"},
                     "issue": ({"issue_active_pct": prof.get("issue_active_pct"), "warp_instructions": prof.get("warp_instructions"),
                                "avg_threads_per_instruction": prof.get("avg_threads_per_instruction"),
-                               "source": "ncu --set full, profiles/r1_c3_step6_frustum_pipeline_ncu.txt"} if prof else None)}
+                               "source": "ncu --set full, profiles/r1_c3_final_ncu.txt"} if prof else None)}
         if world == 1 and not args.no_cpu:
             arm = CpuArm(sc, tw, th, budget_s=12.0)
             dt = arm.run()
