@@ -698,6 +698,24 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 		CUU(cudaStreamSynchronize(st));     /* flat's vectors die at the end of this block */
 	}
 	CUU(cudaStreamSynchronize(st));         /* the caller frees its arrays right after (render.cc:96-103) */
+	{
+		/* culling slack of the leaves from the conditioning of their triangles (box_slack); ill-shaped triangles
+		 * are rare, and only then is the slack pushed up the tree, one level per pass */
+		unsigned int *fat = c->d_counter.as<unsigned int>() + 2;
+		CUU(cudaMemsetAsync(fat, 0, sizeof(unsigned int), st));
+		const unsigned grid = (unsigned)((num_pairs + 255) / 256);
+		k_slack_leaves<<<grid, 256, 0, st>>>(c->d_pairs.as<float4>(), c->d_tris.as<float4>(), (uint32_t)num_pairs, (uint32_t)pair_stride, fat);
+		CUU(cudaGetLastError());
+		unsigned int h_fat = 0;
+		CUU(cudaMemcpyAsync(&h_fat, fat, sizeof h_fat, cudaMemcpyDeviceToHost, st));
+		CUU(cudaStreamSynchronize(st));
+		if (h_fat) {
+			for (uint32_t pass = 0; pass < depth; ++pass)
+				k_slack_relax<<<grid, 256, 0, st>>>(c->d_pairs.as<float4>(), (uint32_t)num_pairs, (uint32_t)pair_stride);
+			CUU(cudaGetLastError());
+			CUU(cudaStreamSynchronize(st));
+		}
+	}
 #undef CUU
 
 	c->sc.pairs = c->d_pairs.as<float4>();

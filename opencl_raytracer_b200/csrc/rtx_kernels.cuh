@@ -103,18 +103,36 @@ __device__ __noinline__ void walk_reference(const SceneDev &sc, f3 o, f3 d, floa
  * ------------------------------------------------------------------------ */
 struct Slab { float tmin, tmax; };
 
-/* Culling slack of a box, stored in the pad lane of its 32-byte node.  The reference accepts a hit whose
- * parametric coordinates lie up to 1e-5 outside the triangle (intersect_kernel.cl:96,101), i.e. up to ~1e-5 of
- * the triangle's extent outside its leaf box, so the ray can hit the triangle at parameter r and enter the
- * triangle's box only LATER, at r + overshoot / |d_k| along the axis k it overshoots.  A box may therefore be
- * skipped against the best hit so far only if  t_min - slack * max_k |1 / d_k|  lies beyond the culling bound,
- * with slack >= the overshoot of any triangle inside: 2.5e-4 of the box's largest extent (25 x the nominal
- * tolerance, for the rounding of s and t on thin triangles) + 4e-6 of its largest coordinate (rounding of P). */
-__host__ __device__ __forceinline__ float box_slack(float lx, float ly, float lz, float hx, float hy, float hz)
+/* Culling slack of a box, stored in the pad lane of its 32-byte node.  The reference tests a triangle whenever
+ * its leaf box passes the slab test and accepts the hit wherever the plane point P lies, as long as the computed
+ * s, t are within 1e-5 of the triangle (intersect_kernel.cl:96,101).  So P can lie outside the triangle's own leaf
+ * box: by ~1e-5 of the triangle's extent for a well-shaped triangle, by more when s and t are ill-conditioned
+ * (s = (uv wv - vv wu) / D loses ~eps * kappa, kappa = uu vv / |D| = 1 / sin^2 of the angle between the edges), and
+ * anywhere in the plane once D is rounding noise.  The ray then hits the triangle at parameter r but enters the
+ * triangle's box only at r + overshoot / |d_k| along the axis k it overshoots.  A box may therefore be skipped
+ * against the best hit so far only if  t_min - slack * max_k |1 / d_k|  lies beyond the culling bound, with
+ * slack >= the overshoot of any triangle inside the box:
+ *   interior box   2.5e-4 of its largest extent + 4e-6 of its largest coordinate (25 x the nominal tolerance; the
+ *                  second term covers the rounding of P itself), raised to the largest slack among its leaves;
+ *   leaf           max(2.5e-4, 1e-5 kappa) of the extent, and +inf (never skipped) for kappa > 1e4 or D == 0.
+ * tools/fuzz_gpu.py (needle meshes) and tests/test_parity_gpu.py hold this against the literal walk. */
+#define RTX_SLACK_REL 2.5e-4f
+__host__ __device__ __forceinline__ float box_slack_rel(float lx, float ly, float lz, float hx, float hy, float hz, float rel)
 {
 	const float ext = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz);
 	const float mag = fmaxf(fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy))), fmaxf(fabsf(lz), fabsf(hz)));
-	return 2.5e-4f * ext + 4e-6f * mag;
+	return rel * ext + 4e-6f * mag;
+}
+__host__ __device__ __forceinline__ float box_slack(float lx, float ly, float lz, float hx, float hy, float hz)
+{
+	return box_slack_rel(lx, ly, lz, hx, hy, hz, RTX_SLACK_REL);
+}
+/* relative slack of one triangle from its record q3 = (uu, uv, vv, D) */
+RTX_DEV float tri_slack_rel(float4 q3)
+{
+	const float kappa = (q3.x * q3.z) / fabsf(q3.w);
+	if (!(kappa <= 1e4f)) return __int_as_float(0x7f800000);            /* ill-conditioned, D == 0 or NaN: never cull */
+	return fmaxf(RTX_SLACK_REL, 1e-5f * kappa);
 }
 
 /* Slab interval of one box.  Same products as the literal test ((bb - o) * (1/d), one rounding each);
@@ -523,6 +541,8 @@ RTX_DEV void collect_frustum(const SceneDev &sc, const Frustum &f, int *__restri
 			const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
 			const bool pL = frustum_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, f, eL);
 			const bool pR = frustum_box(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, f, eR);
+			eL -= q1.w;                 /* a hit may lie up to the box's slack in front of the box (box_slack) */
+			eR -= q3.w;
 			refL = __float_as_int(q1.z); refR = __float_as_int(q3.z);
 			iL = pL && refL >= 0; fL = pL && refL < 0;
 			iR = pR && refR >= 0; fR = pR && refR < 0;
@@ -1477,6 +1497,42 @@ __global__ void k_deinterleave(const float *__restrict__ gathered, uint32_t worl
 }
 
 /* ------------------- device-side pieces of the flatten ------------------- */
+
+/* Leaf slots of the node pairs get the slack of their triangles (tri_slack_rel), in all four octant copies;
+ * *fat = 1 if any leaf needs more than the default, so that k_slack_relax has something to propagate. */
+__global__ void k_slack_leaves(float4 *__restrict__ pairs, const float4 *__restrict__ tris, uint32_t num_pairs, uint32_t stride, unsigned int *fat)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= num_pairs) return;
+	for (int k = 0; k < 2; ++k) {
+		const float4 a = pairs[4 * (size_t)p + 2 * k], b = pairs[4 * (size_t)p + 2 * k + 1];
+		const int ref = __float_as_int(b.z);
+		if (ref >= 0) continue;
+		const uint32_t enc = ~(uint32_t)ref, first = enc >> 3, count = (enc & 7u) + 1u;
+		float rel = RTX_SLACK_REL;
+		for (uint32_t t = first; t < first + count; ++t) rel = fmaxf(rel, tri_slack_rel(tris[4 * (size_t)t + 3]));
+		if (rel == RTX_SLACK_REL) continue;
+		const float slack = box_slack_rel(a.x, a.y, a.z, a.w, b.x, b.y, rel);      /* copy 0 is unswapped: (lo.xyz, hi.x), (hi.y, hi.z) */
+		for (int v = 0; v < 4; ++v) pairs[((size_t)v * stride + p) * 4 + 2 * k + 1].w = slack;
+		*fat = 1u;
+	}
+}
+
+/* One bottom-up relaxation step: the slack of a child slot is at least the slack of the child pair's own slots.
+ * Run `depth` times (only when k_slack_leaves found a fat leaf). */
+__global__ void k_slack_relax(float4 *__restrict__ pairs, uint32_t num_pairs, uint32_t stride)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= num_pairs) return;
+	for (int k = 0; k < 2; ++k) {
+		const float4 b = pairs[4 * (size_t)p + 2 * k + 1];
+		const int ref = __float_as_int(b.z);
+		if (ref < 0) continue;
+		const float child = fmaxf(pairs[4 * (size_t)ref + 1].w, pairs[4 * (size_t)ref + 3].w);
+		if (child > b.w)
+			for (int v = 0; v < 4; ++v) pairs[((size_t)v * stride + p) * 4 + 2 * k + 1].w = child;
+	}
+}
 
 /* --------------------------------------------------------------------------
  * Upload, device side: the invariants of the reference's pre-order tree (bvh.cc:98-162) and the two

@@ -251,6 +251,20 @@ def random_soup(ntris: int, seed: int = 1, extent: float = 1.5, size: float = 0.
     return _finish(verts, faces)
 
 
+def needle_soup(ntris: int, seed: int = 1, extent: float = 1.2):
+    """Needle / sliver triangles: the third vertex lies 1e-5 .. 1e-2 edge lengths off the first edge, so
+    D = uv^2 - uu vv of intersect_kernel.cl:93 is nearly rounding noise and the computed (s, t) of a plane hit are
+    ill-conditioned: the reference then accepts "hits" far outside the triangle's own box (culling)."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-extent, extent, (ntris, 3))
+    a = rng.normal(size=(ntris, 3)); a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b = rng.normal(size=(ntris, 3)); b /= np.linalg.norm(b, axis=1, keepdims=True)
+    L = rng.uniform(0.2, 1.5, (ntris, 1))
+    eps = 10.0 ** rng.uniform(-5, -2, (ntris, 1))
+    t = np.stack([c, c + a * L, c + a * L * rng.uniform(0.3, 0.7, (ntris, 1)) + b * L * eps], 1)
+    return _finish(t.reshape(-1, 3), np.arange(3 * ntris, dtype=np.int64).reshape(-1, 3))
+
+
 def quad_wall(z: float = -1.0, half: float = 10.0):
     """Two triangles sharing a diagonal (the reference bunny's ground plane in miniature)."""
     v = np.array([[-half, -half, z], [half, -half, z], [half, half, z], [-half, half, z]], np.float64)
