@@ -121,6 +121,7 @@ __host__ __device__ __forceinline__ float box_slack_rel(float lx, float ly, floa
 {
 	const float ext = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz);
 	const float mag = fmaxf(fmaxf(fmaxf(fabsf(lx), fabsf(hx)), fmaxf(fabsf(ly), fabsf(hy))), fmaxf(fabsf(lz), fabsf(hz)));
+	if (!(rel <= 3e38f)) return rel;                          /* +inf stays +inf for a box of zero extent too (inf * 0) */
 	return rel * ext + 4e-6f * mag;
 }
 __host__ __device__ __forceinline__ float box_slack(float lx, float ly, float lz, float hx, float hy, float hz)
@@ -543,6 +544,8 @@ RTX_DEV void collect_frustum(const SceneDev &sc, const Frustum &f, int *__restri
 			const bool pR = frustum_box(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, f, eR);
 			eL -= q1.w;                 /* a hit may lie up to the box's slack in front of the box (box_slack) */
 			eR -= q3.w;
+			if (!(eL == eL)) eL = __int_as_float(0xff800000);          /* keys must stay ordered: no NaN */
+			if (!(eR == eR)) eR = __int_as_float(0xff800000);
 			refL = __float_as_int(q1.z); refR = __float_as_int(q3.z);
 			iL = pL && refL >= 0; fL = pL && refL < 0;
 			iR = pR && refR >= 0; fR = pR && refR < 0;

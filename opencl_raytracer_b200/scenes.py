@@ -265,6 +265,25 @@ def needle_soup(ntris: int, seed: int = 1, extent: float = 1.2):
     return _finish(t.reshape(-1, 3), np.arange(3 * ntris, dtype=np.int64).reshape(-1, 3))
 
 
+def degenerate_soup(ntris: int, seed: int = 1):
+    """A soup in which 15 % of the triangles repeat a vertex (zero area, zero-extent boxes when all three coincide),
+    15 % have collinear vertices and 10 % are 1e-7-sized specks: D = 0 and n = 0 cases of intersect_kernel.cl:70-93."""
+    rng = np.random.default_rng(seed)
+    v, f = random_soup(ntris, seed=int(rng.integers(1 << 30)), size=0.4)
+    t = v.astype(np.float64).reshape(-1, 3, 3)
+    which = rng.random(t.shape[0])
+    rep = which < 0.15
+    t[rep, 2] = t[rep, 1]
+    point = which < 0.03
+    t[point, 1] = t[point, 0]
+    t[point, 2] = t[point, 0]
+    col = (which >= 0.15) & (which < 0.3)
+    t[col, 2] = t[col, 0] + (t[col, 1] - t[col, 0]) * rng.uniform(-1, 2, (int(col.sum()), 1))
+    speck = (which >= 0.3) & (which < 0.4)
+    t[speck] = t[speck, :1] + (t[speck] - t[speck, :1]) * 1e-7
+    return _finish(t.reshape(-1, 3), f)
+
+
 def quad_wall(z: float = -1.0, half: float = 10.0):
     """Two triangles sharing a diagonal (the reference bunny's ground plane in miniature)."""
     v = np.array([[-half, -half, z], [half, -half, z], [half, half, z], [-half, half, z]], np.float64)

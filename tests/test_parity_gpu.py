@@ -380,6 +380,33 @@ def test_needle_triangles(po, scene_mod, ntris, seed):
             assert np.array_equal(fid, rr.face_id) and np.array_equal(dist, rr.distance)
 
 
+@pytest.mark.parametrize("ntris,seed,w,h_,ss", [(4000, 5, 200, 120, 9), (1000, 2, 256, 256, 1)])
+def test_degenerate_triangles(po, scene_mod, ntris, seed, w, h_, ss):
+    """Zero-area, collinear and speck triangles (D = 0, n = 0, zero-extent leaf boxes): their leaves carry an infinite
+    culling slack, which must stay +inf (not inf * 0 = NaN) so that the depth-sorted candidate lists stay ordered.
+    Found by tools/fuzz_gpu.py: NaN keys scrambled the rank sort and whole packets lost their candidates."""
+    host = require_gpu()
+    from opencl_raytracer_b200 import scenes
+    v, f = scenes.degenerate_soup(ntris, seed=seed)
+    sc = scene_mod.scene_from_mesh(v, f, name="degenerate")
+    rt = host.RayTracer(host.Options(width=w, height=h_, nSuperSamples=ss))
+    ref = po.render(sc, rt.totalWidth, rt.totalHeight, 1.0, True)
+    assert (ref.face_id != host.NO_HIT).mean() > 0.5
+    for tun in ({}, {host.TUNE_FRUSTUM: 1}, {host.TUNE_FRUSTUM: 1, host.TUNE_LIST_RAYS_PER_THREAD: 4}, {host.TUNE_FRUSTUM: 0},
+                {host.TUNE_LEAF_SIZE: 4, host.TUNE_FRUSTUM: 1}):
+        with host.CudaHost(rt) as h:
+            for k, val in tun.items():
+                h.set_tunable(k, val)
+            h.set_tunable(host.TUNE_RECORD_HITS, 1)
+            h.upload_scene(sc)
+            h()
+            fid, dist = h.download_hits()
+            assert np.array_equal(fid, ref.face_id), (tun, int((fid != ref.face_id).sum()))
+            assert np.array_equal(dist, ref.distance)
+            img = h.download()
+            assert np.array_equal(np.isnan(img), np.isnan(ref.image)) and np.array_equal(np.nan_to_num(img), np.nan_to_num(ref.image))
+
+
 def test_arbitrary_ray_kernels_agree_on_a_large_batch(sibenik_scene):
     """2^26 generated rays: the refill kernel and the plain while-while kernel give the same hit count and id sum."""
     host = require_gpu()

@@ -17,7 +17,7 @@ from oracle import pyoracle as po  # noqa: E402
 
 
 def make_mesh(rng):
-    kind = rng.integers(0, 6)
+    kind = rng.integers(0, 8)
     n = int(rng.choice([30, 200, 1000, 4000]))
     if kind == 0:        # plain soup
         v, f = scenes.random_soup(n, seed=int(rng.integers(1 << 30)), size=float(rng.choice([0.05, 0.35, 1.0])))
@@ -51,6 +51,15 @@ def make_mesh(rng):
         parts = [scenes.icosphere(rng.uniform(-1, 1, 3) * [1, 1, 0.5], float(rng.uniform(0.1, 0.8)), int(rng.integers(1, 5))) for _ in range(int(rng.integers(1, 5)))]
         v, f = scenes._merge(parts)
         return np.asarray(v, np.float64), np.asarray(f), "spheres"
+    if kind == 6:        # degenerate triangles: zero area (repeated vertices), collinear vertices, 1e-7-sized specks
+        v, f = scenes.degenerate_soup(n, seed=int(rng.integers(1 << 30)))
+        return v.astype(np.float64), f, "degenerate"
+    if kind == 7:        # far from the origin: large coordinates, small triangles (rounding of P dominates)
+        v, f = scenes.random_soup(n, seed=int(rng.integers(1 << 30)), size=0.02, extent=0.6)
+        v = v.astype(np.float64)
+        v[:, 2] = v[:, 2] * 0.2 - float(rng.choice([50.0, 400.0]))        # a thin slab 50 or 400 units down the -z axis
+        v[:, :2] *= float(rng.choice([20.0, 150.0]))
+        return v, f, "far"
     v, f = scenes.sibenik_standin(detail=float(rng.choice([0.2, 0.35])))
     return v.astype(np.float64), f, "standin"
 
