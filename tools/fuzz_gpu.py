@@ -103,6 +103,16 @@ def main():
         res = render_all(sc, rt, [EX] + fast, jitter)
         base = res[0]
         bad = 0
+        # the literal walk on the GPU against the CPU oracle (a row sample when the frame is large)
+        step = max(1, (rt.totalWidth * rt.totalHeight) // 150000)
+        rows = (int(rng.integers(0, step)), rt.totalHeight, step)
+        ref = po.render(sc, rt.totalWidth, rt.totalHeight, po.focal_roundtrip(focal), True, jitter_seed=jitter, rows=rows)
+        sel = slice(*rows)
+        nb = int((base[2][0][sel] != ref.face_id[sel]).sum()) + int((base[2][1][sel] != ref.distance[sel]).sum()) + \
+            int(((base[1][sel] != ref.image[sel]) & ~(np.isnan(base[1][sel]) & np.isnan(ref.image[sel]))).sum())
+        if nb:
+            bad += nb
+            print("  MISMATCH seed %d literal GPU walk vs CPU oracle: %d differences" % (seed, nb), flush=True)
         for name, img, (fid, dist), _ in res[1:]:
             nb = int((fid != base[2][0]).sum()) + int((dist != base[2][1]).sum()) + int(((img != base[1]) & ~(np.isnan(img) & np.isnan(base[1]))).sum())
             if nb:
@@ -129,8 +139,8 @@ def main():
                         bad += nb
                         print("  MISMATCH seed %d rays %-8s max_distance %g: %d differences" % (seed, name, md, nb), flush=True)
         # ambient occlusion against the CPU oracle (small frame)
-        if seed % 4 == 0:
-            ao = po.Ao.make(method=int(rng.integers(0, 2)), samples=int(rng.integers(1, 4)), max_distance=float(0.1 * np.abs(hi - lo).max() * rng.choice([0.3, 1.0])))
+        if True:
+            ao = po.Ao.make(method=seed % 2, samples=int(rng.integers(1, 4)), max_distance=float(0.1 * np.abs(hi - lo).max() * rng.choice([0.1, 0.3, 1.0, 5.0])))
             rta = host.RayTracer(host.Options(width=48, height=32, nSuperSamples=4, focalLength=focal, enableAO=True, aoNumSamples=ao.samples,
                                               aoMethod=ao.method, aoMaxDistance=float(ao.max_distance)))
             with host.CudaHost(rta) as h:
@@ -143,6 +153,31 @@ def main():
             if nb:
                 bad += nb
                 print("  MISMATCH seed %d ambient occlusion method %d samples %d: %d pixels" % (seed, ao.method, ao.samples, nb), flush=True)
+        # tile partition (emulated ranks on one GPU) and the pipelined download
+        if seed % 3 == 0:
+            import torch
+            world = int(rng.choice([2, 3, 5]))
+            tx, ty, tpr = host.tile_layout(rt.totalWidth, rt.totalHeight, world)
+            gathered = torch.zeros(world * tpr * 1024, dtype=torch.float32, device="cuda")
+            ctxs = [host.CudaHost(rt, jitter_seed=jitter, tile_rank=r, tile_world=world) for r in range(world)]
+            for r, c in enumerate(ctxs):
+                c.upload_scene(sc)
+                c.bind_output(gathered[r * tpr * 1024:(r + 1) * tpr * 1024].data_ptr(), tpr * 1024)
+                c()
+            torch.cuda.synchronize()
+            ctxs[0].deinterleave_async(gathered.data_ptr(), world)
+            ctxs[0].synchronize()
+            img = ctxs[0].download()
+            for c in ctxs:
+                c.close()
+            nb = int(((img != base[1]) & ~(np.isnan(img) & np.isnan(base[1]))).sum())
+            with host.CudaHost(rt, jitter_seed=jitter) as h:
+                h.upload_scene(sc)
+                img = h.render_download()
+            nb += int(((img != base[1]) & ~(np.isnan(img) & np.isnan(base[1]))).sum())
+            if nb:
+                bad += nb
+                print("  MISMATCH seed %d tile partition (world %d) / render_download: %d pixels" % (seed, world, nb), flush=True)
         hitfrac = float((base[2][0] != host.NO_HIT).mean())
         print("seed %3d %-10s scale %-6g %4d tris depth %2d  %dx%d s=%d f=%.1f jitter %d  hit %.2f  %s" % (
             seed, kind, scale, sc.num_triangles, base[3], w, hgt, ss, focal, int(jitter != 0), hitfrac, "ok" if bad == 0 else "BAD (%d)" % bad), flush=True)
