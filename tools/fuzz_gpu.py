@@ -97,6 +97,8 @@ def main():
         sc = scn.scene_from_mesh(v.astype(np.float32), f, name=kind)
         w, hgt = [(64, 48), (97, 61), (200, 120), (33, 200), (256, 256)][int(rng.integers(0, 5))]
         ss = int(rng.choice([1, 4, 9, 16]))
+        if seed % 8 == 5:                      # a frame with >= 10 000 tiles: the two-level (super-tile) frustum pass
+            w, hgt, ss = [(1920, 1080, 4), (2500, 1300, 4), (1000, 900, 16)][int(rng.integers(0, 3))]
         focal = float(rng.choice([0.3, 1.0, 1.0, 2.5]))
         jitter = int(rng.choice([0, 0, 0x5EED]))
         rt = host.RayTracer(host.Options(width=w, height=hgt, nSuperSamples=ss, focalLength=focal))
