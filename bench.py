@@ -41,7 +41,14 @@ WORKLOADS = {
     "c3": (3840, 2160, 16, "sibenik", "C3 sibenik-standin 3840x2160 s=16 (15360x8640 = 132.7M rays, regular grid)"),
     "c2": (1920, 1080, 4, "sibenik", "C2 sibenik-standin 1920x1080 s=4 (3840x2160 = 8.29M rays)"),
     "c1": (600, 600, 4, "bunny", "C1 bunny 600x600 s=4 (1200x1200 = 1.44M rays)"),
+    "c4": (3840, 2160, 1, "bunny_x144", "C4 bunny subdivided x144 (10.16M triangles, 20.3M nodes) 3840x2160 s=1 (8.29M rays)"),
+    # C5 is not a frame: 2^28 generated rays against the C2 tree, sharded by contiguous index ranges (bench_c5)
+    "c5": (32, 32, 1, "sibenik", "C5 2^28 random-direction rays vs the sibenik stand-in tree (counter-hash generator, seed 1234)"),
 }
+
+
+METRIC = {"c3": "Mrays/s closest-hit (sibenik, 4K)", "c2": "Mrays/s closest-hit (sibenik, 1080p s=4)",
+          "c1": "Mrays/s closest-hit (bunny, reference defaults)", "c4": "Mrays/s closest-hit (bunny x144, 4K)"}
 
 
 def load_peaks():
@@ -54,10 +61,12 @@ def load_peaks():
 
 def build_scene(kind):
     from opencl_raytracer_b200 import scene, scenes
-    if kind == "bunny":
+    if kind in ("bunny", "bunny_x144"):
         from oracle import pyoracle as po          # only for the staged reference mesh file
         v, f = po.read_mesh_bin(po.staged_bunny_path())
-        return scene.scene_from_mesh(v, f, name="bunny")
+        if kind == "bunny_x144":
+            v, f = scenes.subdivided(v, f)
+        return scene.scene_from_mesh(v, f, name=kind)
     v, f = scenes.sibenik_standin()
     return scene.scene_from_mesh(v, f, name="sibenik_standin")
 
@@ -158,6 +167,107 @@ def oracle_counters(sc, tw, th):
     return c["V"], c["T"], c["h"]
 
 
+def bench_c5(args, rank, world, local_rank, desc):
+    """Config C5: 2^28 arbitrary rays, generated on the device from the counter hash, sharded over the ranks by
+    contiguous index ranges; the only exchange is the all-reduce of the (hit count, face-id sum) checksums."""
+    import torch
+    import torch.distributed as dist
+    from opencl_raytracer_b200 import host
+    import __graft_entry__ as g
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        g.build(quiet=True)
+    if world > 1:
+        dist.barrier()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    sc = build_scene("sibenik")
+    total = 1 << 28
+    per = total // world
+    first = rank * per
+    rt = host.RayTracer(host.Options(width=32, height=32, nSuperSamples=1))
+    h = host.CudaHost(rt, device=local_rank)
+    h.upload_scene(sc)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sums = torch.zeros(2, dtype=torch.int64, device=dev)
+    for _ in range(args.warmup):
+        h.trace_random_rays(1234, first, per)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ms, checks = [], None
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        hits, idsum, _, _ = h.trace_random_rays(1234, first, per)       # blocking; device time in stats (CUDA events on its stream)
+        ms = torch.tensor([h.stats()["kernel_ms"]], dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sums[0], sums[1] = hits, idsum
+        e0.record()
+        if world > 1:
+            dist.all_reduce(sums)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms += e0.elapsed_time(e1)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        step_ms.append(float(ms.item()))
+        checks = (int(sums[0].item()), int(sums[1].item()))
+    clocks = sampler.result()
+    parity = cpu = roofline = None
+    if rank == 0:
+        from oracle import pyoracle as po
+        lo, hi = sc.root_box()
+        n_chk = 1 << 16
+        o, d = po.gen_random_rays(1234, 0, n_chk, lo, hi)
+        ref = po.trace_rays(sc, o, d, 100000.0, want_counters=True)
+        _, _, fid, dist_ = h.trace_random_rays(1234, 0, n_chk, want_arrays=True)
+        parity = {"rays_checked": n_chk, "id_mismatches": int((fid != ref.face_id).sum()), "distance_mismatches": int((dist_ != ref.distance).sum()),
+                  "hit_count": checks[0], "face_id_sum": checks[1]}
+        V, T, hf = ref.counters["V"], ref.counters["T"], ref.counters["h"]
+        B = 32.0 * V + 48.0 * T + 48.0 * hf + 4.0 + 8.0
+        peak, peak_src = load_peaks()
+        kms = float(np.mean(step_ms))
+        achieved = B * per / (kms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": 16990208,
+                    "peak_source": peak_src, "kernel": "k_trace_persistent (refill kernel)", "kernel_ms": kms, "algorithmic_bytes_per_ray": B,
+                    "V": V, "T": T, "h": hf,
+                    "note": "tree is L2-resident: DRAM traffic per launch is 17 MB (profiles/r1_c5_refill_ncu.txt); the kernel is bound by the L1 "
+                            "data pipe (96 %: 32 different node pairs per warp load)"}
+        if world == 1 and not args.no_cpu:
+            import time as _t
+            n_cpu = 1 << 22
+            o, d = po.gen_random_rays(1234, 0, n_cpu, lo, hi)
+            t0 = _t.perf_counter()
+            po.trace_rays(sc, o, d, 100000.0)
+            dt = _t.perf_counter() - t0
+            cpu = {"value": n_cpu / dt / 1e6, "unit": "Mrays/s", "cores": int(po.port().orc_online_cpus()), "kind": "port",
+                   "sample": "first 2^22 rays of the batch, %.2f s" % dt}
+    h.close()
+    if rank == 0:
+        t = float(np.sum(step_ms))
+        print(json.dumps({
+            "metric": "Mrays/s closest-hit (random rays vs sibenik BVH)", "value": total * args.steps / (t * 1e-3) / 1e6, "unit": "Mrays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "scene": sc.name, "triangles": sc.num_triangles, "rays_per_step": total,
+                       "parallelism": "contiguous ray-index ranges over %d GPU(s), tree replicated, 1 all-reduce of the checksums" % world,
+                       "l2": "flushed between timed iterations (256 MiB memset, untimed)"},
+            "clocks": clocks, "e2e": {"value": total * args.steps / (t * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16,
+                                      "calls": "rtx_trace_random_rays: rays generated on the device, only the checksums come back"},
+            "gpu_launches": args.steps * world, "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "step_ms": step_ms}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,6 +287,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     width, height, nss, scene_kind, desc = WORKLOADS[args.workload]
+    if args.workload == "c5" and args.impl != "reference":
+        return bench_c5(args, rank, world, local_rank, desc)
 
     if args.impl == "reference":
         if rank != 0:
@@ -196,7 +308,7 @@ def main():
         info = arm.info(v, float(np.mean(times)))
         rays_per_step = arm.nrays
         print(json.dumps({
-            "impl": "reference", "metric": "Mrays/s closest-hit (sibenik, 4K)", "value": v, "unit": "Mrays/s",
+            "impl": "reference", "metric": METRIC.get(args.workload, METRIC["c3"]), "value": v, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": rays_per_step / v / 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -465,7 +577,7 @@ def main():
 
     if rank == 0:
         print(json.dumps({
-            "metric": "Mrays/s closest-hit (sibenik, 4K)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "metric": METRIC.get(args.workload, METRIC["c3"]), "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "scene": sc.name, "triangles": sc.num_triangles, "rays_per_step": rays,
