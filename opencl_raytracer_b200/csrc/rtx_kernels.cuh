@@ -1055,7 +1055,8 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 			if (__ballot_sync(full, descending) == 0u) break;
 			if (descending) {
 				const float4 *q = sc.pairs + 4 * (size_t)r.cur;
-				const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+				const f4x2 qa = ldg256(q), qb = ldg256(q + 2);
+				const float4 q0 = qa.a, q1 = qa.b, q2 = qb.a, q3 = qb.b;
 				if (COUNT) visits += 2;
 				const Slab L = slab_interval<false, 4>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r.o, r.id);
 				const Slab R = slab_interval<false, 4>(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, r.o, r.id);
@@ -1092,7 +1093,8 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 				const float4 *q = sc.tris + 4 * (size_t)tri;
 				TriHit h;
 				if (COUNT) ++tests;
-				if (!triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), r.o, r.d, r.cull, h)) continue;
+				const f4x2 ta = ldg256(q), tb = ldg256(q + 2);
+				if (!triangle_test(ta.a, ta.b, tb.a, tb.b, r.o, r.d, r.cull, h)) continue;
 				if (!(h.dist < r.best.dist || (h.dist == r.best.dist && tri < r.best.tri))) continue;
 				if (sc.verify_leafbox) {
 					const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
