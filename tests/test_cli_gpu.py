@@ -45,6 +45,27 @@ def test_reference_cli_writes_the_reference_pgm(tmp_path, scene_mod, soup_golden
         assert np.array_equal(read_pgm(pgm), a["u8_" + name]), name
 
 
+@pytest.mark.gpu
+def test_reference_cli_on_the_bunny_with_default_options(tmp_path, scene_mod, po, bunny_scene):
+    """Config C1 exactly as a user types it: `./render bunny.off out.pgm` -- 600x600, s=4, shading, uniform ambient
+    occlusion with 3 rings -- through the unmodified render.cc / mesh.cc / bvh.cc and the shadow opencl_host.h.
+    The OFF text is rewritten from the staged reference mesh (9 significant digits round-trip float32)."""
+    require_gpu()
+    if not os.path.exists(CLI):
+        pytest.skip("oracle/_ref/render_b200 not built (reference tree absent at build time)")
+    v, f = po.read_mesh_bin(po.staged_bunny_path())
+    off, pgm = str(tmp_path / "bunny.off"), str(tmp_path / "bunny.pgm")
+    scene_mod.write_off(off, v, f)
+    res = subprocess.run([CLI, off, pgm], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    ref = po.render(bunny_scene, 1200, 1200, 1.0, True, ao=po.Ao.make())
+    assert np.array_equal(read_pgm(pgm), po.resize(ref.image, 600, 600, 2))
+    res = subprocess.run([CLI, "-a", "0", off, pgm], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    ref = po.render(bunny_scene, 1200, 1200, 1.0, True)
+    assert np.array_equal(read_pgm(pgm), po.resize(ref.image, 600, 600, 2))
+
+
 def test_reference_cli_fails_loudly_without_a_device(tmp_path, scene_mod, soup_golden):
     from opencl_raytracer_b200 import host
     if host.device_count() > 0:
