@@ -569,6 +569,19 @@ def main():
                     "issue": ({"issue_active_pct": prof.get("issue_active_pct"), "warp_instructions": prof.get("warp_instructions"),
                                "avg_threads_per_instruction": prof.get("avg_threads_per_instruction"),
                                "source": "ncu --set full, profiles/r1_c3_final_ncu.txt"} if prof else None)}
+        if prof.get("warp_instructions") and prof.get("duration_ms") and clocks.get("sm_mhz"):
+            # the bound that actually holds: warp instructions issued per second against 4 schedulers x 1 instruction
+            # per clock per SM.  Instruction count from the ncu capture of this kernel (fixed for the workload),
+            # time and clock measured in this run.
+            sms = host.device_info(local_rank).sm_count
+            list_ms = kernel_ms_mean * (prof.get("share_of_kernel_ms_pct", 100.0) / 100.0) if world == 1 else None
+            if list_ms:
+                ach = prof["warp_instructions"] / (list_ms * 1e-3) / 1e9
+                pk = sms * 4 * clocks["sm_mhz"] * 1e6 / 1e9
+                roofline["issue_roofline"] = {"bound": "warp-instruction issue", "achieved": ach, "peak": pk, "unit": "Gwarp-instr/s", "frac": ach / pk,
+                                              "how": "warp instructions of the list kernel (ncu, %s) / (kernel_ms x its %.1f %% share of the event pair); "
+                                                     "peak = %d SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the timed region)"
+                                                     % (prof.get("source", "profiles/"), prof.get("share_of_kernel_ms_pct", 100.0), sms, clocks["sm_mhz"])}
         if world == 1 and not args.no_cpu:
             arm = CpuArm(sc, tw, th, budget_s=12.0)
             dt = arm.run()
