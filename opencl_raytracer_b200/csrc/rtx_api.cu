@@ -830,7 +830,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 	}
 	const uint32_t launches_per_pass = w.frustum ? 2u : 1u;
 	const size_t frame_bytes = (size_t)c->W * c->H * sizeof(float);
-	uint32_t nbands = 1;
+	uint32_t nbands = 1, passes = 1;
 	if (host_dst && !c->ao && c->local_tiles > 0) {
 		nbands = (uint32_t)(frame_bytes / (8u << 20));             /* >= 8 MB per copy keeps PCIe near its rate */
 		if (nbands > RTX_MAX_BANDS) nbands = RTX_MAX_BANDS;
@@ -843,8 +843,15 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 		for (uint32_t b = 0; b < nbands; ++b)
 			if (!c->band_ev[b]) CU(c, cudaEventCreateWithFlags(&c->band_ev[b], cudaEventDisableTiming));
 		const float *src = w.image;
+		passes = 0;
 		for (uint32_t b = 0; b < nbands; ++b) {
-			const uint32_t r0 = (uint32_t)((uint64_t)c->tiles_y * b / nbands), r1 = (uint32_t)((uint64_t)c->tiles_y * (b + 1) / nbands);
+			/* the first band is a quarter of the others: the copy engine starts early and never waits afterwards
+			 * (a band's copy takes longer than the next band's tracing) */
+			const uint64_t den = 4ull * nbands - 3;
+			const uint32_t r0 = b == 0 ? 0u : (uint32_t)((uint64_t)c->tiles_y * (4ull * b - 3) / den);
+			const uint32_t r1 = (uint32_t)((uint64_t)c->tiles_y * (4ull * (b + 1) - 3) / den);
+			if (r1 == r0) continue;
+			++passes;
 			w.tile_begin = r0 * c->tiles_x;
 			w.tile_count = (r1 - r0) * c->tiles_x;
 			w.num_units = w.tile_count * 32u;
@@ -862,7 +869,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 	} else {
 		CU(c, launch_render(c, w, st));
 	}
-	c->stats.kernel_launches += launches_per_pass * nbands;
+	c->stats.kernel_launches += launches_per_pass * passes;
 	uint32_t ao_launches = 0;
 	if (c->ao && w.num_units > 0) {
 		/* second pass over the hit pixels (intersect_kernel.cl:305-307) */
