@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "rtx_kernels.cuh"
+#include "rtx_build.cuh"
 
 namespace {
 
@@ -80,6 +81,11 @@ struct rtx_ctx {
 	SceneDev sc{};
 	DevBuf d_pairs, d_tris, d_leafbox, d_tnormals, d_ref_nodes, d_ref_aabbs;
 	DevBuf t_faces, t_verts, t_vnormals, t_scan;   /* upload staging, kept between uploads */
+	DevBuf t_build, d_triangles;                   /* rtx_upload_mesh: builder work space; leaf order -> input face id */
+	uint32_t build_levels = 0;
+	double build_ms = 0.0;
+	bool tree_on_device = false;                   /* d_ref_* / t_faces / d_triangles hold a complete reference tree */
+	size_t tree_nodes = 0, tree_tris = 0;
 	TreeResult h_tree{};         /* result words of the device-side tree check (k_tree_*) */
 	f3 bbmin{}, bbmax{};
 	uint32_t tree_depth = 0;
@@ -559,7 +565,7 @@ void rtx_destroy(rtx_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
-	DevBuf *bufs[] = { &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
+	DevBuf *bufs[] = { &c->t_build, &c->d_triangles, &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
 	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists, &c->d_slists, &c->d_raytab,
 	                   &c->d_hit_st, &c->d_ao_ring };
 	for (DevBuf *b : bufs) b->release();
@@ -605,43 +611,25 @@ int rtx_set_tunable(rtx_ctx *c, int which, int64_t v)
 	return RTX_OK;
 }
 
-int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_t *nodes, size_t nnodes,
-               const float *aabbs16, size_t naabbvec, const float *verts16, size_t nverts,
-               const float *vnormals16, size_t nnormals)
+/* Everything after the five reference arrays are in device memory (copied by rtx_upload or built by
+ * rtx_upload_mesh): validation, prefix counts, flatten, culling slack.  faces/nodes/aabbs16 are the host copies the
+ * host flatten reads; NULL when the tree only exists on the device.  nodes0 = nodes[0], root_box8 = the root's
+ * (min, max) vectors. */
+static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nverts, uint32_t nodes0, const float *root_box8,
+                         const uint32_t *faces, const uint32_t *nodes, const float *aabbs16)
 {
-	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
-	if (!faces || !nodes || !aabbs16 || !verts16 || !vnormals16) return fail(c, RTX_ERR_ARG, "null array");
-	if (nfaceidx == 0 || nfaceidx % 3 != 0) return fail(c, RTX_ERR_ARG, "faces must hold 3 indices per triangle");
-	const size_t ntris = nfaceidx / 3;
-	if (naabbvec != 2 * nnodes) return fail(c, RTX_ERR_ARG, "aabbs must hold 2 vectors per node");
-	if (nverts != nnormals || nverts == 0) return fail(c, RTX_ERR_ARG, "one normal per vertex required");
-	if (ntris >= (1u << 28)) return fail(c, RTX_ERR_ARG, "too many triangles (limit 2^28)");
-	CU(c, cudaSetDevice(c->device));
-	c->uploaded = false;
-	cudaStream_t st = c->stream;
 #define CUU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(c, e_, #call); } while (0)
-	CUU(c->t_faces.alloc(nfaceidx * 4));
-	CUU(c->t_verts.alloc(nverts * 16));
-	CUU(c->t_vnormals.alloc(nverts * 16));
-	CUU(c->d_ref_nodes.alloc(nnodes * 4));
-	CUU(c->d_ref_aabbs.alloc(nnodes * 32));
-	CUU(c->d_tris.alloc(ntris * 64));
-	CUU(c->d_leafbox.alloc(ntris * 32));
-	CUU(c->d_tnormals.alloc(ntris * 48));
-	CUU(cudaMemcpyAsync(c->t_faces.p, faces, nfaceidx * 4, cudaMemcpyHostToDevice, st));
-	CUU(cudaMemcpyAsync(c->t_verts.p, verts16, nverts * 16, cudaMemcpyHostToDevice, st));
-	CUU(cudaMemcpyAsync(c->t_vnormals.p, vnormals16, nverts * 16, cudaMemcpyHostToDevice, st));
-	CUU(cudaMemcpyAsync(c->d_ref_nodes.p, nodes, nnodes * 4, cudaMemcpyHostToDevice, st));
-	CUU(cudaMemcpyAsync(c->d_ref_aabbs.p, aabbs16, nnodes * 32, cudaMemcpyHostToDevice, st));
-	/* the copies above are in flight while the host validates and scans */
 	const bool device_flatten = c->flatten_on_device && c->top_smem == 0;
+	const size_t ntris = nfaceidx / 3;
+	cudaStream_t st = c->stream;
+	if (!device_flatten && !nodes) return fail(c, RTX_ERR_UNSUPPORTED, "the host flatten (RTX_TUNE_TOP_SMEM / RTX_TUNE_FLATTEN_ON_DEVICE = 0) needs the tree on the host: use rtx_upload");
 	std::string why;
 	size_t num_pairs = 0, pair_stride = 0;
 	uint32_t depth = 0, top_pairs = 0;
 	if (device_flatten) {
 		/* The tree's invariants, the two prefix counts k_flatten_nodes needs and the depth of the
 		 * flattened tree are all computed on the device from the raw arrays (k_tree_*): no host pass over the nodes. */
-		if (nnodes == 0 || nodes[0] != nnodes || (nnodes & 1) == 0 || leaves_of((uint32_t)nnodes) != ntris)
+		if (nnodes == 0 || nodes0 != nnodes || (nnodes & 1) == 0 || leaves_of((uint32_t)nnodes) != ntris)
 			return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: node count must be 2*triangles-1 and nodes[0] must equal it");
 		const uint32_t K = (uint32_t)c->leaf_size, n = (uint32_t)nnodes;
 		pair_stride = ntris > 1 ? ntris - 1 : 1;                       /* internal nodes of a full binary tree: the bound for any K */
@@ -738,16 +726,165 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	c->sc.top_pairs = c->top_smem > 0 ? top_pairs : 0;
 	c->sc.num_tris = (uint32_t)ntris;
 	c->sc.verify_leafbox = c->leaf_size > 1 ? 1u : 0u;
-	c->bbmin = make_f3(aabbs16[0], aabbs16[1], aabbs16[2]);
-	c->bbmax = make_f3(aabbs16[4], aabbs16[5], aabbs16[6]);
+	c->bbmin = make_f3(root_box8[0], root_box8[1], root_box8[2]);
+	c->bbmax = make_f3(root_box8[4], root_box8[5], root_box8[6]);
 	float scale = 0.f;
-	for (int k = 0; k < 3; ++k) scale = std::fmax(scale, std::fmax(std::fabs(aabbs16[k]), std::fabs(aabbs16[4 + k])));
+	for (int k = 0; k < 3; ++k) scale = std::fmax(scale, std::fmax(std::fabs(root_box8[k]), std::fabs(root_box8[4 + k])));
 	c->sc.scene_scale = scale;
 	c->tree_depth = depth;
 	c->stats.tree_depth = depth;
 	c->stats.num_pairs = (uint32_t)num_pairs;
 	c->uploaded = true;
 	c->rendered = false;
+	return RTX_OK;
+}
+
+int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_t *nodes, size_t nnodes,
+               const float *aabbs16, size_t naabbvec, const float *verts16, size_t nverts,
+               const float *vnormals16, size_t nnormals)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (!faces || !nodes || !aabbs16 || !verts16 || !vnormals16) return fail(c, RTX_ERR_ARG, "null array");
+	if (nfaceidx == 0 || nfaceidx % 3 != 0) return fail(c, RTX_ERR_ARG, "faces must hold 3 indices per triangle");
+	const size_t ntris = nfaceidx / 3;
+	if (naabbvec != 2 * nnodes) return fail(c, RTX_ERR_ARG, "aabbs must hold 2 vectors per node");
+	if (nverts != nnormals || nverts == 0) return fail(c, RTX_ERR_ARG, "one normal per vertex required");
+	if (ntris >= (1u << 28)) return fail(c, RTX_ERR_ARG, "too many triangles (limit 2^28)");
+	CU(c, cudaSetDevice(c->device));
+	c->uploaded = false;
+	c->tree_on_device = false;
+	cudaStream_t st = c->stream;
+#define CUU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(c, e_, #call); } while (0)
+	CUU(c->t_faces.alloc(nfaceidx * 4));
+	CUU(c->t_verts.alloc(nverts * 16));
+	CUU(c->t_vnormals.alloc(nverts * 16));
+	CUU(c->d_ref_nodes.alloc(nnodes * 4));
+	CUU(c->d_ref_aabbs.alloc(nnodes * 32));
+	CUU(c->d_tris.alloc(ntris * 64));
+	CUU(c->d_leafbox.alloc(ntris * 32));
+	CUU(c->d_tnormals.alloc(ntris * 48));
+	CUU(cudaMemcpyAsync(c->t_faces.p, faces, nfaceidx * 4, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->t_verts.p, verts16, nverts * 16, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->t_vnormals.p, vnormals16, nverts * 16, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->d_ref_nodes.p, nodes, nnodes * 4, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->d_ref_aabbs.p, aabbs16, nnodes * 32, cudaMemcpyHostToDevice, st));
+	/* the copies above are in flight while the device validates and scans */
+	return upload_finish(c, nfaceidx, nnodes, nverts, nodes[0], aabbs16, faces, nodes, aabbs16);
+#undef CUU
+}
+
+/* Mesh in, everything else on the device: the reference's longest-axis builder (bvh.cc:59-162) level by level
+ * (rtx_build.cuh), then the same validation / flatten as rtx_upload.  Emits the arrays bvh.cc would (rtx_download_tree). */
+int rtx_upload_mesh(rtx_ctx *c, const float *verts16, size_t nverts, const uint32_t *faces, size_t nfaces, const float *vnormals16)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (!verts16 || !faces || !vnormals16) return fail(c, RTX_ERR_ARG, "null array");
+	if (nfaces == 0 || nverts == 0) return fail(c, RTX_ERR_ARG, "empty mesh");
+	if (nfaces >= (1u << 28)) return fail(c, RTX_ERR_ARG, "too many triangles (limit 2^28)");
+	if (!(c->flatten_on_device && c->top_smem == 0)) return fail(c, RTX_ERR_UNSUPPORTED, "rtx_upload_mesh needs the device flatten (no RTX_TUNE_TOP_SMEM)");
+	CU(c, cudaSetDevice(c->device));
+	c->uploaded = false;
+	c->tree_on_device = false;
+	cudaStream_t st = c->stream;
+	const uint32_t N = (uint32_t)nfaces;
+	const size_t nnodes = 2 * (size_t)N - 1;
+#define CUU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(c, e_, #call); } while (0)
+	CUU(c->t_faces.alloc((size_t)N * 12));
+	CUU(c->t_verts.alloc(nverts * 16));
+	CUU(c->t_vnormals.alloc(nverts * 16));
+	CUU(c->d_ref_nodes.alloc(nnodes * 4));
+	CUU(c->d_ref_aabbs.alloc(nnodes * 32));
+	CUU(c->d_triangles.alloc((size_t)N * 4));
+	CUU(c->d_tris.alloc((size_t)N * 64));
+	CUU(c->d_leafbox.alloc((size_t)N * 32));
+	CUU(c->d_tnormals.alloc((size_t)N * 48));
+	/* work space: input faces, per-triangle centroid / lo / hi, two copies of (ids, segments, accumulators), scan, partials, flags */
+	const uint32_t per_block = RTX_BVH_BLOCK * RTX_BVH_ITEMS, nblocks = (N + per_block - 1) / per_block;
+	const size_t words = (size_t)N * (3 + 9 + 2 * (1 + 3 + RTX_BVH_ACC) + 1) + 1 + nblocks + 8;
+	CUU(c->t_build.alloc(words * 4));
+	uint32_t *p = c->t_build.as<uint32_t>();
+	uint32_t *in_faces = p;                      p += (size_t)N * 3;
+	float *tc = reinterpret_cast<float *>(p);    p += (size_t)N * 3;
+	float *tlo = reinterpret_cast<float *>(p);   p += (size_t)N * 3;
+	float *thi = reinterpret_cast<float *>(p);   p += (size_t)N * 3;
+	uint32_t *ids[2]; BvhSeg *seg[2]; uint32_t *acc[2];
+	for (int k = 0; k < 2; ++k) {
+		ids[k] = p;                              p += N;
+		seg[k] = reinterpret_cast<BvhSeg *>(p);  p += (size_t)N * 3;
+		acc[k] = p;                              p += (size_t)N * RTX_BVH_ACC;
+	}
+	uint32_t *scan = p;                          p += (size_t)N + 1;
+	uint32_t *partials = p;                      p += nblocks;
+	unsigned int *live = p, *bad_face = p + 1;
+	CUU(cudaMemcpyAsync(in_faces, faces, (size_t)N * 12, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->t_verts.p, verts16, nverts * 16, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemcpyAsync(c->t_vnormals.p, vnormals16, nverts * 16, cudaMemcpyHostToDevice, st));
+	CUU(cudaMemsetAsync(live, 0, 2 * sizeof(unsigned int), st));
+	CUU(cudaEventRecord(c->ev0, st));
+	const unsigned grid = (N + 255) / 256;
+	k_bvh_prepare<<<grid, 256, 0, st>>>(in_faces, c->t_verts.as<float4>(), N, (uint32_t)nverts, tc, tlo, thi, ids[0], seg[0], acc[0], bad_face);
+	CUU(cudaGetLastError());
+	uint32_t levels = 0;
+	int cur = 0;
+	unsigned int h_flags[2] = { N > 1 ? 1u : 0u, 0u };
+	while (h_flags[0] != 0) {
+		if (++levels > N) return cudaStreamSynchronize(st), fail(c, RTX_ERR_CUDA, "BVH build did not terminate");
+		k_bvh_accumulate<<<grid, 256, 0, st>>>(ids[cur], seg[cur], N, tc, tlo, thi, acc[cur]);
+		k_bvh_split<<<grid, 256, 0, st>>>(seg[cur], N, acc[cur], c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>());
+		k_bvh_flag_partials<<<nblocks, RTX_BVH_BLOCK, 0, st>>>(ids[cur], seg[cur], acc[cur], tc, N, partials);
+		k_bvh_spine<<<1, 32, 0, st>>>(partials, nblocks);
+		k_bvh_flag_scan<<<nblocks, RTX_BVH_BLOCK, 0, st>>>(ids[cur], seg[cur], acc[cur], tc, N, partials, scan);
+		CUU(cudaMemsetAsync(live, 0, sizeof(unsigned int), st));
+		k_bvh_scatter<<<grid, 256, 0, st>>>(ids[cur], seg[cur], acc[cur], tc, scan, N, ids[cur ^ 1], seg[cur ^ 1], acc[cur ^ 1], live);
+		CUU(cudaGetLastError());
+		CUU(cudaMemcpyAsync(h_flags, live, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+		CUU(cudaStreamSynchronize(st));
+		cur ^= 1;
+	}
+	k_bvh_leaves<<<grid, 256, 0, st>>>(ids[cur], seg[cur], N, tlo, thi, in_faces, c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>(),
+	                                   c->d_triangles.as<uint32_t>(), c->t_faces.as<uint32_t>());
+	CUU(cudaGetLastError());
+	CUU(cudaEventRecord(c->ev1, st));
+	float root_box[8];
+	uint32_t nodes0 = 0;
+	CUU(cudaMemcpyAsync(root_box, c->d_ref_aabbs.p, sizeof root_box, cudaMemcpyDeviceToHost, st));
+	CUU(cudaMemcpyAsync(&nodes0, c->d_ref_nodes.p, sizeof nodes0, cudaMemcpyDeviceToHost, st));
+	CUU(cudaMemcpyAsync(h_flags, live, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+	CUU(cudaStreamSynchronize(st));
+	if (h_flags[1]) return fail(c, RTX_ERR_ARG, "face index out of range");
+	float ms = 0.f;
+	if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->build_ms = ms;
+	c->build_levels = levels;
+	const int rc = upload_finish(c, (size_t)N * 3, nnodes, nverts, nodes0, root_box, nullptr, nullptr, nullptr);
+	if (rc == RTX_OK) { c->tree_on_device = true; c->tree_nodes = nnodes; c->tree_tris = N; }
+	return rc;
+#undef CUU
+}
+
+/* The tree of the last upload in the reference's own formats (bvh.h:15-17 + the leaf-ordered faces of
+ * render.cc:88-95); any pointer may be NULL.  nodes: 2T-1 words, aabbs16: 2(2T-1) vectors of 4 floats,
+ * triangles: T words (leaf order -> input face id; only after rtx_upload_mesh), sorted_faces: 3T words. */
+int rtx_download_tree(rtx_ctx *c, uint32_t *nodes, float *aabbs16, uint32_t *triangles, uint32_t *sorted_faces)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (!c->uploaded) return fail(c, RTX_ERR_STATE, "no scene uploaded");
+	if (triangles && !c->tree_on_device) return fail(c, RTX_ERR_STATE, "the leaf-order triangle ids exist only after rtx_upload_mesh");
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaStreamSynchronize(c->stream));
+	const size_t T = c->sc.num_tris, n = 2 * T - 1;
+	if (nodes) CU(c, cudaMemcpy(nodes, c->d_ref_nodes.p, n * 4, cudaMemcpyDeviceToHost));
+	if (aabbs16) CU(c, cudaMemcpy(aabbs16, c->d_ref_aabbs.p, n * 32, cudaMemcpyDeviceToHost));
+	if (triangles) CU(c, cudaMemcpy(triangles, c->d_triangles.p, T * 4, cudaMemcpyDeviceToHost));
+	if (sorted_faces) CU(c, cudaMemcpy(sorted_faces, c->t_faces.p, T * 12, cudaMemcpyDeviceToHost));
+	return RTX_OK;
+}
+
+/* device time of the last rtx_upload_mesh build (prepare .. leaves) and the number of levels it took */
+int rtx_build_stats(const rtx_ctx *c, double *build_ms, uint32_t *levels)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	if (build_ms) *build_ms = c->build_ms;
+	if (levels) *levels = c->build_levels;
 	return RTX_OK;
 }
 

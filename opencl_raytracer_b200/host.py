@@ -36,6 +36,7 @@ ABI_SYMBOLS = (
     "rtx_synchronize", "rtx_download_hits", "rtx_download_u8", "rtx_device_image", "rtx_trace_rays",
     "rtx_trace_rays_device", "rtx_trace_random_rays", "rtx_tile_layout", "rtx_deinterleave_async", "rtx_bind_output",
     "rtx_probe_bandwidth", "rtx_resize_u8_async", "rtx_deinterleave_u8_async", "rtx_render_download",
+    "rtx_upload_mesh", "rtx_download_tree", "rtx_build_stats",
 )
 
 
@@ -98,6 +99,12 @@ def load_library():
     lib.rtx_create.argtypes = [C.POINTER(vp), C.POINTER(_Options)]
     lib.rtx_upload.restype = C.c_int
     lib.rtx_upload.argtypes = [vp, u32p, C.c_size_t, u32p, C.c_size_t, fp, C.c_size_t, fp, C.c_size_t, fp, C.c_size_t]
+    lib.rtx_upload_mesh.restype = C.c_int
+    lib.rtx_upload_mesh.argtypes = [vp, fp, C.c_size_t, u32p, C.c_size_t, fp]
+    lib.rtx_download_tree.restype = C.c_int
+    lib.rtx_download_tree.argtypes = [vp, u32p, fp, u32p, u32p]
+    lib.rtx_build_stats.restype = C.c_int
+    lib.rtx_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
     lib.rtx_render.restype = C.c_int
     lib.rtx_render.argtypes = [vp]
     lib.rtx_download.restype = C.c_int
@@ -262,6 +269,36 @@ class CudaHost:
 
     def upload_scene(self, scene: Scene):
         self.upload(scene.faces, scene.nodes, scene.aabbs, scene.vertices, scene.normals)
+        self._ntris = scene.num_triangles
+
+    def upload_mesh(self, vertices, faces, vnormals):
+        """Raw mesh in (vertices / vnormals with the 16-byte Vec3f stride, faces in input order): the reference's
+        longest-axis BVH is built on the device (rtx_upload_mesh) -- no host tree."""
+        vertices = np.ascontiguousarray(vertices, np.float32)
+        vnormals = np.ascontiguousarray(vnormals, np.float32)
+        faces = np.ascontiguousarray(faces, np.uint32)
+        self._ck(self._lib.rtx_upload_mesh(self._ctx, vertices.ctypes.data, vertices.size // 4, faces.ctypes.data, faces.size // 3,
+                                           vnormals.ctypes.data))
+        self._ntris = faces.size // 3
+
+    def download_tree(self, want_triangles: bool = True):
+        """(nodes, aabbs, triangles, sorted_faces) of the last upload, in the formats of bvh.h:15-17 / render.cc:88-95."""
+        s = Stats()
+        self._ck(self._lib.rtx_get_stats(self._ctx, C.byref(s)))
+        t = getattr(self, "_ntris", None) or (s.num_pairs + 1)
+        n = 2 * t - 1
+        nodes = np.empty(n, np.uint32)
+        aabbs = np.empty((2 * n, 4), np.float32)
+        tri = np.empty(t, np.uint32) if want_triangles else None
+        faces = np.empty(3 * t, np.uint32)
+        self._ck(self._lib.rtx_download_tree(self._ctx, nodes.ctypes.data, aabbs.ctypes.data,
+                                             tri.ctypes.data if want_triangles else None, faces.ctypes.data))
+        return nodes, aabbs, tri, faces
+
+    def build_stats(self):
+        ms, lv = C.c_double(), C.c_uint32()
+        self._ck(self._lib.rtx_build_stats(self._ctx, C.byref(ms), C.byref(lv)))
+        return ms.value, lv.value
 
     def __call__(self) -> bool:
         self._ck(self._lib.rtx_render(self._ctx))
