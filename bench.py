@@ -530,6 +530,19 @@ def main():
                 hx.upload_scene(sc)
                 ms = kernel_ms(hx)
                 extras[name] = {"kernel_ms": ms, "Mrays/s": rays / ms / 1e3}
+        with host.CudaHost(rt, device=local_rank) as hx:                  # the tree itself built on the device
+            hx.upload_mesh(sc.vertices, sc.orig_faces, sc.normals)
+            t0 = time.perf_counter()
+            hx.upload_mesh(sc.vertices, sc.orig_faces, sc.normals)
+            wall = (time.perf_counter() - t0) * 1e3
+            bms, levels = hx.build_stats()
+            nodes_d, aabbs_d, tri_d, faces_d = hx.download_tree()
+            extras["device_bvh_build"] = {"build_ms": bms, "levels": levels, "rtx_upload_mesh_wall_ms": wall,
+                                          "identical_to_host_builder": bool(np.array_equal(nodes_d, sc.nodes) and np.array_equal(tri_d, sc.triangles)
+                                                                            and np.array_equal(faces_d, sc.faces)
+                                                                            and np.array_equal(aabbs_d.view(np.uint32), np.ascontiguousarray(sc.aabbs, np.float32).reshape(-1, 4).view(np.uint32))),
+                                          "what": "rtx_upload_mesh: the reference's longest-axis builder (bvh.cc:59-162) level by level on the device, "
+                                                  "then the same validation + flatten as rtx_upload"}
         extras["reference_algorithm_on_gpu"]["what"] = ("k_render_exhaustive: the reference kernel's own algorithm (one thread per pixel, "
                                                         "stackless pre-order walk, no culling) compiled for sm_100a")
 
