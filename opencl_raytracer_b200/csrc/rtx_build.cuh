@@ -44,8 +44,9 @@ __global__ void k_bvh_prepare(const uint32_t *__restrict__ faces, const float4 *
 #pragma unroll
 	for (int k = 0; k < 3; ++k) {
 		tc[3 * (size_t)t + k] = rn_div(rn_add(rn_add(a[k], b[k]), c[k]), 3.0f);
-		tlo[3 * (size_t)t + k] = fminf(a[k], fminf(b[k], c[k]));
-		thi[3 * (size_t)t + k] = fmaxf(a[k], fmaxf(b[k], c[k]));
+		const float mbc = c[k] < b[k] ? c[k] : b[k], Mbc = b[k] < c[k] ? c[k] : b[k];     /* std::min / std::max keep the FIRST of equals */
+		tlo[3 * (size_t)t + k] = mbc < a[k] ? mbc : a[k];                                 /* triangle.cc:7-22 */
+		thi[3 * (size_t)t + k] = a[k] < Mbc ? Mbc : a[k];
 	}
 	ids[t] = t;
 	seg[t] = BvhSeg{ 0u, ntris, 0u };
