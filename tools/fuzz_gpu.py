@@ -2,7 +2,8 @@
 the GPU (k_render_exhaustive = the reference's algorithm, no re-ordering, no culling), over random meshes that
 stress the parity argument: needle and sliver triangles, shared edges (ties), coplanar duplicates, scenes scaled
 by 1e-3 .. 1e3, grids whose edges line up with pixel columns, odd image sizes, extreme focal lengths; plus
-arbitrary rays (both kernels vs the literal walk) and ambient occlusion against the CPU oracle on small frames.
+arbitrary rays (both kernels vs the literal walk), ambient occlusion against the CPU oracle on small frames, and the
+device-built BVH (rtx_upload_mesh) against the host builder's arrays.
 
 usage: python tools/fuzz_gpu.py [first_seed=0] [count=40]
 """
@@ -155,6 +156,15 @@ def main():
             if nb:
                 bad += nb
                 print("  MISMATCH seed %d ambient occlusion method %d samples %d: %d pixels" % (seed, ao.method, ao.samples, nb), flush=True)
+        # the BVH built on the device from the raw mesh == the host builder's arrays, bit for bit
+        with host.CudaHost(rt, jitter_seed=jitter) as h:
+            h.upload_mesh(sc.vertices, sc.orig_faces, sc.normals)
+            nodes_d, aabbs_d, tri_d, faces_d = h.download_tree()
+            nb = int((nodes_d != sc.nodes).sum()) + int((tri_d != sc.triangles).sum()) + int((faces_d != sc.faces).sum()) + \
+                int((aabbs_d.view(np.uint32) != np.ascontiguousarray(sc.aabbs, np.float32).reshape(-1, 4).view(np.uint32)).sum())
+            if nb:
+                bad += nb
+                print("  MISMATCH seed %d device-built tree vs host builder: %d words" % (seed, nb), flush=True)
         # tile partition (emulated ranks on one GPU) and the pipelined download
         if seed % 3 == 0:
             import torch
