@@ -139,11 +139,14 @@ int rtx_upload(rtx_ctx *ctx,
  * The reference's longest-axis BVH (src/bvh.cc:59-162: centroid-box midpoint cut, stable partition, one triangle per
  * leaf) is built on the device, level by level, and yields the arrays bvh.cc would -- rtx_download_tree returns them
  * -- so everything downstream is unchanged.  Replaces BVH::buildBVH + the face sort of render.cc:88-95 + rtx_upload
- * for callers that are not bound to the reference's host code. */
+ * for callers that are not bound to the reference's host code.  vnormals16 == NULL: the vertex normals are computed
+ * on the device too (compute_vertex_normals, src/mesh.cc:95-139, same additions in the same order);
+ * rtx_download_normals returns them. */
 int rtx_upload_mesh(rtx_ctx *ctx, const float *verts16, size_t nverts, const uint32_t *faces, size_t nfaces,
                     const float *vnormals16);
 int rtx_download_tree(rtx_ctx *ctx, uint32_t *nodes, float *aabbs16, uint32_t *triangles, uint32_t *sorted_faces);
 int rtx_build_stats(const rtx_ctx *ctx, double *build_ms, uint32_t *levels);
+int rtx_download_normals(rtx_ctx *ctx, float *vnormals16, size_t nverts);   /* the normals of the last rtx_upload_mesh */
 
 /* Launch the traversal over this context's share of the image and wait. */
 int rtx_render(rtx_ctx *ctx);

@@ -778,8 +778,9 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 int rtx_upload_mesh(rtx_ctx *c, const float *verts16, size_t nverts, const uint32_t *faces, size_t nfaces, const float *vnormals16)
 {
 	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
-	if (!verts16 || !faces || !vnormals16) return fail(c, RTX_ERR_ARG, "null array");
+	if (!verts16 || !faces) return fail(c, RTX_ERR_ARG, "null array");
 	if (nfaces == 0 || nverts == 0) return fail(c, RTX_ERR_ARG, "empty mesh");
+	if (nverts >= 0xfffffff0ull) return fail(c, RTX_ERR_ARG, "too many vertices");
 	if (nfaces >= (1u << 28)) return fail(c, RTX_ERR_ARG, "too many triangles (limit 2^28)");
 	if (!(c->flatten_on_device && c->top_smem == 0)) return fail(c, RTX_ERR_UNSUPPORTED, "rtx_upload_mesh needs the device flatten (no RTX_TUNE_TOP_SMEM)");
 	CU(c, cudaSetDevice(c->device));
@@ -818,10 +819,33 @@ int rtx_upload_mesh(rtx_ctx *c, const float *verts16, size_t nverts, const uint3
 	unsigned int *live = p, *bad_face = p + 1;
 	CUU(cudaMemcpyAsync(in_faces, faces, (size_t)N * 12, cudaMemcpyHostToDevice, st));
 	CUU(cudaMemcpyAsync(c->t_verts.p, verts16, nverts * 16, cudaMemcpyHostToDevice, st));
-	CUU(cudaMemcpyAsync(c->t_vnormals.p, vnormals16, nverts * 16, cudaMemcpyHostToDevice, st));
 	CUU(cudaMemsetAsync(live, 0, 2 * sizeof(unsigned int), st));
 	CUU(cudaEventRecord(c->ev0, st));
 	const unsigned grid = (N + 255) / 256;
+	if (vnormals16) {
+		CUU(cudaMemcpyAsync(c->t_vnormals.p, vnormals16, nverts * 16, cudaMemcpyHostToDevice, st));
+	} else {
+		/* compute_vertex_normals (mesh.cc:95-139) on the device, same additions in the same (face) order */
+		const uint32_t V = (uint32_t)nverts, vblocks = (V + per_block - 1) / per_block;
+		const size_t need = (size_t)N * 4 + (size_t)N * 3 + 3 * ((size_t)V + 1) + vblocks + 8;
+		CUU(c->t_scan.alloc(need * 4));                    /* upload_finish re-uses t_scan afterwards */
+		uint32_t *w = c->t_scan.as<uint32_t>();
+		float4 *fnormal = reinterpret_cast<float4 *>(w);   w += (size_t)N * 4;
+		uint32_t *list = w;                                w += (size_t)N * 3;
+		uint32_t *count = w;                               w += (size_t)V + 1;
+		uint32_t *offset = w;                              w += (size_t)V + 1;
+		uint32_t *cursor = w;                              w += (size_t)V + 1;
+		uint32_t *vpart = w;
+		CUU(cudaMemsetAsync(count, 0, ((size_t)V + 1) * 4, st));
+		CUU(cudaMemsetAsync(cursor, 0, ((size_t)V + 1) * 4, st));
+		k_vn_faces<<<grid, 256, 0, st>>>(in_faces, c->t_verts.as<float4>(), N, V, fnormal, count);
+		k_scan_partials<<<vblocks, RTX_BVH_BLOCK, 0, st>>>(count, V, vpart);
+		k_bvh_spine<<<1, 32, 0, st>>>(vpart, vblocks);
+		k_scan_apply<<<vblocks, RTX_BVH_BLOCK, 0, st>>>(count, V, vpart, offset);
+		k_vn_fill<<<grid, 256, 0, st>>>(in_faces, N, V, offset, cursor, list);
+		k_vn_vertices<<<(V + 127) / 128, 128, 0, st>>>(offset, list, fnormal, V, c->t_vnormals.as<float4>());
+		CUU(cudaGetLastError());
+	}
 	k_bvh_prepare<<<grid, 256, 0, st>>>(in_faces, c->t_verts.as<float4>(), N, (uint32_t)nverts, tc, tlo, thi, ids[0], seg[0], acc[0], bad_face);
 	CUU(cudaGetLastError());
 	uint32_t levels = 0;
@@ -876,6 +900,17 @@ int rtx_download_tree(rtx_ctx *c, uint32_t *nodes, float *aabbs16, uint32_t *tri
 	if (aabbs16) CU(c, cudaMemcpy(aabbs16, c->d_ref_aabbs.p, n * 32, cudaMemcpyDeviceToHost));
 	if (triangles) CU(c, cudaMemcpy(triangles, c->d_triangles.p, T * 4, cudaMemcpyDeviceToHost));
 	if (sorted_faces) CU(c, cudaMemcpy(sorted_faces, c->t_faces.p, T * 12, cudaMemcpyDeviceToHost));
+	return RTX_OK;
+}
+
+int rtx_download_normals(rtx_ctx *c, float *vnormals16, size_t nverts)
+{
+	if (!c || !vnormals16) return fail(c, RTX_ERR_ARG, "null argument");
+	if (!c->tree_on_device) return fail(c, RTX_ERR_STATE, "normals are kept only after rtx_upload_mesh");
+	if (nverts * 16 > c->t_vnormals.bytes) return fail(c, RTX_ERR_ARG, "more vertices than were uploaded");
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaStreamSynchronize(c->stream));
+	CU(c, cudaMemcpy(vnormals16, c->t_vnormals.p, nverts * 16, cudaMemcpyDeviceToHost));
 	return RTX_OK;
 }
 

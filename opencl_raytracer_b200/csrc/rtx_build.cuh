@@ -257,3 +257,110 @@ __global__ void k_bvh_leaves(const uint32_t *__restrict__ ids, const BvhSeg *__r
 	sorted_faces[3 * (size_t)i + 1] = faces[3 * t + 1];
 	sorted_faces[3 * (size_t)i + 2] = faces[3 * t + 2];
 }
+
+/* --------------------------------------------------------------------------
+ * Vertex normals on the device: compute_vertex_normals (src/mesh.cc:95-139).  The reference adds each face's
+ * un-normalised normal to its three vertices IN FACE ORDER, so a vertex's sum depends on that order; here every
+ * vertex gets the list of its (face, corner) entries, sorts it and adds in the same order.
+ *   k_vn_faces       per face: (b-a) x (c-a) with one rounding per operation, and its length (skip when 0)
+ *   k_vn_count/fill  per corner: incidence lists by vertex (counting sort; the fill order is arbitrary)
+ *   k_vn_vertices    per vertex: sort its list by entry index, add in order, divide by the length unless 0
+ * ------------------------------------------------------------------------ */
+__global__ void k_vn_faces(const uint32_t *__restrict__ faces, const float4 *__restrict__ verts, uint32_t nfaces, uint32_t nverts,
+                           float4 *__restrict__ fnormal, uint32_t *__restrict__ count)
+{
+	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= nfaces) return;
+	const uint32_t i0 = faces[3 * (size_t)f], i1 = faces[3 * (size_t)f + 1], i2 = faces[3 * (size_t)f + 2];
+	if (i0 >= nverts || i1 >= nverts || i2 >= nverts) { fnormal[f] = make_float4(0.f, 0.f, 0.f, 0.f); return; }   /* reported by the builder */
+	const float4 A = verts[i0], B = verts[i1], C = verts[i2];
+	const f3 u = make_f3(rn_sub(B.x, A.x), rn_sub(B.y, A.y), rn_sub(B.z, A.z));
+	const f3 v = make_f3(rn_sub(C.x, A.x), rn_sub(C.y, A.y), rn_sub(C.z, A.z));
+	const f3 n = cross3(u, v);
+	const float len = rn_sqrt(dot3(n, n));
+	fnormal[f] = make_float4(n.x, n.y, n.z, len == 0.0f ? 0.0f : 1.0f);
+	atomicAdd(count + i0, 1u);
+	atomicAdd(count + i1, 1u);
+	atomicAdd(count + i2, 1u);
+}
+
+__global__ void k_vn_fill(const uint32_t *__restrict__ faces, uint32_t nfaces, uint32_t nverts, const uint32_t *__restrict__ offset,
+                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ list)
+{
+	const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= nfaces) return;
+	const uint32_t i[3] = { faces[3 * (size_t)f], faces[3 * (size_t)f + 1], faces[3 * (size_t)f + 2] };
+	if (i[0] >= nverts || i[1] >= nverts || i[2] >= nverts) return;
+#pragma unroll
+	for (uint32_t k = 0; k < 3; ++k) list[offset[i[k]] + atomicAdd(cursor + i[k], 1u)] = 3u * f + k;
+}
+
+__global__ void k_vn_vertices(const uint32_t *__restrict__ offset, uint32_t *__restrict__ list, const float4 *__restrict__ fnormal,
+                              uint32_t nverts, float4 *__restrict__ vnormals)
+{
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= nverts) return;
+	const uint32_t b = offset[v], e = offset[v + 1];
+	for (uint32_t i = b + 1; i < e; ++i) {                   /* insertion sort: valences are small */
+		const uint32_t x = list[i];
+		uint32_t j = i;
+		while (j > b && list[j - 1] > x) { list[j] = list[j - 1]; --j; }
+		list[j] = x;
+	}
+	float nx = 0.f, ny = 0.f, nz = 0.f;
+	for (uint32_t i = b; i < e; ++i) {
+		const float4 n = fnormal[list[i] / 3u];
+		if (n.w == 0.0f) continue;                               /* mesh.cc:112-114: zero-length face normals are skipped */
+		nx = rn_add(nx, n.x); ny = rn_add(ny, n.y); nz = rn_add(nz, n.z);
+	}
+	const float len = rn_sqrt(rn_add(rn_add(rn_mul(nx, nx), rn_mul(ny, ny)), rn_mul(nz, nz)));
+	if (len > 0.0f) { nx = rn_div(nx, len); ny = rn_div(ny, len); nz = rn_div(nz, len); }
+	vnormals[v] = make_float4(nx, ny, nz, 0.f);
+}
+
+/* generic exclusive sum of a u32 array (n + 1 outputs: out[n] = total), three launches like the flag scan */
+__global__ void __launch_bounds__(RTX_BVH_BLOCK)
+k_scan_partials(const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ partials)
+{
+	__shared__ uint32_t s[RTX_BVH_BLOCK / 32];
+	const uint32_t base = (blockIdx.x * RTX_BVH_BLOCK + threadIdx.x) * RTX_BVH_ITEMS;
+	uint32_t a = 0;
+	for (uint32_t k = 0; k < RTX_BVH_ITEMS; ++k)
+		if (base + k < n) a += in[base + k];
+	a = __reduce_add_sync(0xffffffffu, a);
+	if ((threadIdx.x & 31u) == 0) s[threadIdx.x >> 5] = a;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t t = 0;
+		for (int w = 0; w < RTX_BVH_BLOCK / 32; ++w) t += s[w];
+		partials[blockIdx.x] = t;
+	}
+}
+
+__global__ void __launch_bounds__(RTX_BVH_BLOCK)
+k_scan_apply(const uint32_t *__restrict__ in, uint32_t n, const uint32_t *__restrict__ partials, uint32_t *__restrict__ out)
+{
+	__shared__ uint32_t s[RTX_BVH_BLOCK / 32];
+	const uint32_t base = (blockIdx.x * RTX_BVH_BLOCK + threadIdx.x) * RTX_BVH_ITEMS;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	uint32_t f[RTX_BVH_ITEMS], a = 0;
+	for (uint32_t k = 0; k < RTX_BVH_ITEMS; ++k) {
+		f[k] = base + k < n ? in[base + k] : 0u;
+		a += f[k];
+	}
+	uint32_t x = a;
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+		if ((int)lane >= o) x += y;
+	}
+	if (lane == 31) s[warp] = x;
+	__syncthreads();
+	uint32_t off = partials[blockIdx.x];
+	for (uint32_t w = 0; w < warp; ++w) off += s[w];
+	off += x - a;
+	for (uint32_t k = 0; k < RTX_BVH_ITEMS; ++k) {
+		if (base + k < n) out[base + k] = off;
+		off += f[k];
+		if (base + k + 1 == n) out[n] = off;
+	}
+}

@@ -36,7 +36,7 @@ ABI_SYMBOLS = (
     "rtx_synchronize", "rtx_download_hits", "rtx_download_u8", "rtx_device_image", "rtx_trace_rays",
     "rtx_trace_rays_device", "rtx_trace_random_rays", "rtx_tile_layout", "rtx_deinterleave_async", "rtx_bind_output",
     "rtx_probe_bandwidth", "rtx_resize_u8_async", "rtx_deinterleave_u8_async", "rtx_render_download",
-    "rtx_upload_mesh", "rtx_download_tree", "rtx_build_stats",
+    "rtx_upload_mesh", "rtx_download_tree", "rtx_build_stats", "rtx_download_normals",
 )
 
 
@@ -103,6 +103,8 @@ def load_library():
     lib.rtx_upload_mesh.argtypes = [vp, fp, C.c_size_t, u32p, C.c_size_t, fp]
     lib.rtx_download_tree.restype = C.c_int
     lib.rtx_download_tree.argtypes = [vp, u32p, fp, u32p, u32p]
+    lib.rtx_download_normals.restype = C.c_int
+    lib.rtx_download_normals.argtypes = [vp, fp, C.c_size_t]
     lib.rtx_build_stats.restype = C.c_int
     lib.rtx_build_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint32)]
     lib.rtx_render.restype = C.c_int
@@ -271,15 +273,25 @@ class CudaHost:
         self.upload(scene.faces, scene.nodes, scene.aabbs, scene.vertices, scene.normals)
         self._ntris = scene.num_triangles
 
-    def upload_mesh(self, vertices, faces, vnormals):
+    def upload_mesh(self, vertices, faces, vnormals=None):
         """Raw mesh in (vertices / vnormals with the 16-byte Vec3f stride, faces in input order): the reference's
-        longest-axis BVH is built on the device (rtx_upload_mesh) -- no host tree."""
+        longest-axis BVH is built on the device (rtx_upload_mesh) -- no host tree.  vnormals=None: the vertex normals
+        of mesh.cc:95-139 are computed on the device as well."""
         vertices = np.ascontiguousarray(vertices, np.float32)
-        vnormals = np.ascontiguousarray(vnormals, np.float32)
+        if vertices.ndim == 2 and vertices.shape[1] == 3:                    # accept plain xyz too
+            vertices = np.concatenate([vertices, np.zeros((vertices.shape[0], 1), np.float32)], 1)
+        if vnormals is not None:
+            vnormals = np.ascontiguousarray(vnormals, np.float32)
         faces = np.ascontiguousarray(faces, np.uint32)
         self._ck(self._lib.rtx_upload_mesh(self._ctx, vertices.ctypes.data, vertices.size // 4, faces.ctypes.data, faces.size // 3,
-                                           vnormals.ctypes.data))
+                                           vnormals.ctypes.data if vnormals is not None else None))
         self._ntris = faces.size // 3
+        self._nverts = vertices.size // 4
+
+    def download_normals(self) -> np.ndarray:
+        out = np.empty((self._nverts, 4), np.float32)
+        self._ck(self._lib.rtx_download_normals(self._ctx, out.ctypes.data, self._nverts))
+        return out
 
     def download_tree(self, want_triangles: bool = True):
         """(nodes, aabbs, triangles, sorted_faces) of the last upload, in the formats of bvh.h:15-17 / render.cc:88-95."""

@@ -21,6 +21,11 @@ def _check(host, po, sc, render=True):
         assert np.array_equal(aabbs.view(np.uint32), np.ascontiguousarray(sc.aabbs, np.float32).reshape(-1, 4).view(np.uint32))
         ms, levels = h.build_stats()
         assert levels >= 1 or sc.num_triangles == 1
+        # mesh.cc:95-139 on the device: same sums in the same order -> the same bits (NaN-free: zero normals stay zero)
+        h.upload_mesh(sc.vertices, sc.orig_faces, None)
+        vn = h.download_normals()
+        assert np.array_equal(vn.view(np.uint32), np.ascontiguousarray(sc.normals, np.float32).reshape(-1, 4).view(np.uint32))
+        assert np.array_equal(h.download_tree()[0], sc.nodes)
         if render:
             h.set_tunable(host.TUNE_RECORD_HITS, 1)
             h()

@@ -158,8 +158,14 @@ def main():
                 print("  MISMATCH seed %d ambient occlusion method %d samples %d: %d pixels" % (seed, ao.method, ao.samples, nb), flush=True)
         # the BVH built on the device from the raw mesh == the host builder's arrays, bit for bit
         with host.CudaHost(rt, jitter_seed=jitter) as h:
-            h.upload_mesh(sc.vertices, sc.orig_faces, sc.normals)
+            h.upload_mesh(sc.vertices, sc.orig_faces, None if seed % 2 else sc.normals)
             nodes_d, aabbs_d, tri_d, faces_d = h.download_tree()
+            if seed % 2:
+                vn = h.download_normals()
+                nbn = int((vn.view(np.uint32) != np.ascontiguousarray(sc.normals, np.float32).reshape(-1, 4).view(np.uint32)).sum())
+                if nbn:
+                    bad += nbn
+                    print("  MISMATCH seed %d device vertex normals vs host: %d words" % (seed, nbn), flush=True)
             nb = int((nodes_d != sc.nodes).sum()) + int((tri_d != sc.triangles).sum()) + int((faces_d != sc.faces).sum()) + \
                 int((aabbs_d.view(np.uint32) != np.ascontiguousarray(sc.aabbs, np.float32).reshape(-1, 4).view(np.uint32)).sum())
             if nb:
