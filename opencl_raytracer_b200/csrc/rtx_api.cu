@@ -853,6 +853,9 @@ int rtx_upload_mesh(rtx_ctx *c, const float *verts16, size_t nverts, const uint3
 	unsigned int h_flags[2] = { N > 1 ? 1u : 0u, 0u };
 	while (h_flags[0] != 0) {
 		if (++levels > N) return cudaStreamSynchronize(st), fail(c, RTX_ERR_CUDA, "BVH build did not terminate");
+		/* the host looks at the live-segment count every 4th level only: a level without live segments is a no-op
+		 * (every kernel returns at once), a round trip to the host costs as much as a level of a small mesh */
+		const bool look = (levels & 3u) == 0 || N < 4096 || N > (1u << 20);      /* a wasted level of a big mesh costs more than the round trip */
 		k_bvh_accumulate<<<grid, 256, 0, st>>>(ids[cur], seg[cur], N, tc, tlo, thi, acc[cur]);
 		k_bvh_split<<<grid, 256, 0, st>>>(seg[cur], N, acc[cur], c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>());
 		k_bvh_flag_partials<<<nblocks, RTX_BVH_BLOCK, 0, st>>>(ids[cur], seg[cur], acc[cur], tc, N, partials);
@@ -861,8 +864,10 @@ int rtx_upload_mesh(rtx_ctx *c, const float *verts16, size_t nverts, const uint3
 		CUU(cudaMemsetAsync(live, 0, sizeof(unsigned int), st));
 		k_bvh_scatter<<<grid, 256, 0, st>>>(ids[cur], seg[cur], acc[cur], tc, scan, N, ids[cur ^ 1], seg[cur ^ 1], acc[cur ^ 1], live);
 		CUU(cudaGetLastError());
-		CUU(cudaMemcpyAsync(h_flags, live, sizeof h_flags, cudaMemcpyDeviceToHost, st));
-		CUU(cudaStreamSynchronize(st));
+		if (look) {
+			CUU(cudaMemcpyAsync(h_flags, live, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+			CUU(cudaStreamSynchronize(st));
+		}
 		cur ^= 1;
 	}
 	k_bvh_leaves<<<grid, 256, 0, st>>>(ids[cur], seg[cur], N, tlo, thi, in_faces, c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>(),
