@@ -596,6 +596,14 @@ k_frustum_collect_super(const SceneDev sc, const Work w, uint32_t *__restrict__ 
 	const uint32_t st = blockIdx.x * 4 + warp;
 	if (st >= stiles_x * stiles_y) return;
 	const uint32_t sx = st % stiles_x, sy = st / stiles_x;
+	if (w.world > 1) {           /* a rank only needs the super-tiles that hold one of its tiles (warp-uniform test) */
+		bool mine = false;
+		for (uint32_t j = 0; j < RTX_SUPER * RTX_SUPER; ++j) {
+			const uint32_t tx = sx * RTX_SUPER + (j % RTX_SUPER), ty = sy * RTX_SUPER + (j / RTX_SUPER);
+			mine = mine || (tx < w.tiles_x && ty < w.tiles_y && (ty * w.tiles_x + tx) % w.world == w.rank);
+		}
+		if (!mine) return;
+	}
 	const float px = (float)(RTX_TILE * RTX_SUPER);
 	const Frustum f = make_frustum(w.cam, (float)sx * px, (float)sy * px, px, px, sc.scene_scale);
 	collect_frustum(sc, f, s_queue_all[warp], s_tmp_all[warp], s_tkey_all[warp], RTX_SCAP, slists + (size_t)st * RTX_SLIST_STRIDE, lane, nullptr);
