@@ -543,6 +543,14 @@ def main():
                                                                             and np.array_equal(aabbs_d.view(np.uint32), np.ascontiguousarray(sc.aabbs, np.float32).reshape(-1, 4).view(np.uint32))),
                                           "what": "rtx_upload_mesh: the reference's longest-axis builder (bvh.cc:59-162) level by level on the device, "
                                                   "then the same validation + flatten as rtx_upload"}
+        rt_ao = host.RayTracer(host.Options(width=1920, height=1080, nSuperSamples=4, enableAO=True, aoNumSamples=3, aoMethod=0))
+        with host.CudaHost(rt_ao, device=local_rank) as hx:               # the CLI's default options on the C2 frame
+            hx.upload_scene(sc)
+            ms = kernel_ms(hx)
+            hit = float((hx.download() > 0).mean())
+            extras["ambient_occlusion_c2_frame"] = {"kernel_ms": ms, "primary_Mrays/s": rt_ao.totalWidth * rt_ao.totalHeight / ms / 1e3,
+                                                    "what": "3840x2160 primary rays + uniform AO with 3 rings (28 occlusion rays per hit pixel, "
+                                                            "intersect_kernel.cl:214-277); %.1f %% of the pixels are lit" % (100 * hit)}
         extras["reference_algorithm_on_gpu"]["what"] = ("k_render_exhaustive: the reference kernel's own algorithm (one thread per pixel, "
                                                         "stackless pre-order walk, no culling) compiled for sm_100a")
 
