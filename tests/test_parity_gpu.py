@@ -563,3 +563,67 @@ def test_render_download_pipelined(po, sibenik_scene, soup_scene, frustum, rpt):
     with host.CudaHost(rt) as h:
         h.upload_scene(soup_scene)
         assert np.array_equal(h.render_download(), po.render(soup_scene, 128, 96, 1.0, True, ao=ao).image)
+
+
+def test_two_contexts_from_two_host_threads(po, soup_scene, sibenik_scene):
+    """A context is not thread-safe, different contexts are independent (include/rtx_b200.h): two host threads, each
+    with its own context and scene on the same device, upload / render / download concurrently (ctypes releases the
+    GIL during the calls) and both get the oracle's frames every time."""
+    import threading
+    host = require_gpu()
+    jobs = [(soup_scene, host.Options(width=160, height=96, nSuperSamples=4)),
+            (sibenik_scene, host.Options(width=200, height=120, nSuperSamples=4, enableAO=True, aoNumSamples=2, aoMethod=1))]
+    refs = []
+    for sc, opt in jobs:
+        rt = host.RayTracer(opt)
+        ao = po.Ao.make(method=opt.aoMethod, samples=opt.aoNumSamples) if opt.enableAO else None
+        refs.append(po.render(sc, rt.totalWidth, rt.totalHeight, 1.0, True, ao=ao).image)
+    errors = []
+
+    def worker(k):
+        try:
+            sc, opt = jobs[k]
+            rt = host.RayTracer(opt)
+            for rep in range(6):
+                with host.CudaHost(rt) as h:
+                    if rep % 2:
+                        h.upload_mesh(sc.vertices, sc.orig_faces, None)
+                    else:
+                        h.upload_scene(sc)
+                    for _ in range(3):
+                        h()
+                        if not np.array_equal(h.download(), refs[k]):
+                            errors.append("thread %d rep %d: frame differs" % (k, rep))
+                    if not opt.enableAO and not np.array_equal(h.render_download(), refs[k]):
+                        errors.append("thread %d rep %d: pipelined frame differs" % (k, rep))
+        except Exception as e:                                   # noqa: BLE001 -- report from the thread
+            errors.append("thread %d: %r" % (k, e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+
+
+def test_second_device_if_present(po, soup_scene):
+    """rtx_options.device: the same frame on every visible device (skipped on a one-GPU box)."""
+    host = require_gpu()
+    n = host.device_count()
+    if n < 2:
+        pytest.skip("one device visible")
+    rt = host.RayTracer(host.Options(width=128, height=96, nSuperSamples=4))
+    ref = po.render(soup_scene, rt.totalWidth, rt.totalHeight, 1.0, True).image
+    hosts = [host.CudaHost(rt, device=d) for d in range(n)]
+    try:
+        for h in hosts:
+            h.upload_scene(soup_scene)
+        for h in hosts:
+            h()
+        for h in hosts:
+            assert np.array_equal(h.download(), ref)
+            assert np.array_equal(h.render_download(), ref)
+    finally:
+        for h in hosts:
+            h.close()
