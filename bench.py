@@ -249,6 +249,28 @@ def bench_c5(args, rank, world, local_rank, desc):
             dt = _t.perf_counter() - t0
             cpu = {"value": n_cpu / dt / 1e6, "unit": "Mrays/s", "cores": int(po.port().orc_online_cpus()), "kind": "port",
                    "sample": "first 2^22 rays of the batch, %.2f s" % dt}
+    e2e_host = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        # the same kernel fed from HOST arrays (rtx_trace_rays): 32 B/ray up, 8 B/ray down, chunks pipelined over three streams
+        from oracle import pyoracle as po
+        n_host = 1 << 26
+        lo, hi = sc.root_box()
+        o, d = po.gen_random_rays(1234, 0, n_host, lo, hi)            # generator only; not timed
+        o_p, d_p = torch.from_numpy(o).pin_memory().numpy(), torch.from_numpy(d).pin_memory().numpy()
+        del o, d
+        f_p = torch.empty(n_host, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        t_p = torch.empty(n_host, dtype=torch.float32).pin_memory().numpy()
+        h.trace_rays(o_p[:1 << 22], d_p[:1 << 22])
+        import time as _t
+        best = 1e9
+        for _ in range(3):
+            t0 = _t.perf_counter()
+            fid_h, dist_h = h.trace_rays(o_p, d_p, out_face_id=f_p, out_distance=t_p)
+            best = min(best, _t.perf_counter() - t0)
+        _, _, fid_d, _ = h.trace_random_rays(1234, 0, 1 << 20, want_arrays=True)
+        e2e_host = {"value": n_host / best / 1e6, "unit": "Mrays/s", "rays": n_host, "ms": best * 1e3, "h2d_bytes_per_step": n_host * 32,
+                    "d2h_bytes_per_step": n_host * 8, "matches_device_generated_prefix": bool(np.array_equal(fid_h[:1 << 20], fid_d)),
+                    "calls": "rtx_trace_rays(host origins, host directions) -> host face ids + distances; page-locked buffers, chunks of 4 Mi rays pipelined over three streams"}
     h.close()
     if rank == 0:
         t = float(np.sum(step_ms))
@@ -261,6 +283,7 @@ def bench_c5(args, rank, world, local_rank, desc):
                        "l2": "flushed between timed iterations (256 MiB memset, untimed)"},
             "clocks": clocks, "e2e": {"value": total * args.steps / (t * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16,
                                       "calls": "rtx_trace_random_rays: rays generated on the device, only the checksums come back"},
+            "e2e_host_rays": e2e_host,
             "gpu_launches": args.steps * world, "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "step_ms": step_ms}))
     if world > 1:
         dist.barrier()

@@ -198,7 +198,9 @@ int rtx_bind_output(rtx_ctx *ctx, void *device_ptr, size_t count);
 
 /* Closest hit for arbitrary rays (config C5), reference scene_intersect
  * semantics with the given max_distance.  origins/dirs: 4 floats per ray.
- * Host-pointer and device-pointer forms. */
+ * Host-pointer and device-pointer forms.  The host form cuts a large batch into
+ * chunks of 4 Mi rays and overlaps upload, tracing and download of consecutive
+ * chunks on three streams (page-locked host arrays make the copies asynchronous). */
 int rtx_trace_rays(rtx_ctx *ctx, const float *origins, const float *dirs, size_t nrays, float max_distance,
                    uint32_t *face_id, float *distance);
 int rtx_trace_rays_device(rtx_ctx *ctx, const void *d_origins, const void *d_dirs, size_t nrays, float max_distance,

@@ -82,6 +82,9 @@ struct rtx_ctx {
 	DevBuf d_pairs, d_tris, d_leafbox, d_tnormals, d_ref_nodes, d_ref_aabbs;
 	DevBuf t_faces, t_verts, t_vnormals, t_scan;   /* upload staging, kept between uploads */
 	DevBuf t_build, d_triangles;                   /* rtx_upload_mesh: builder work space; leaf order -> input face id */
+	DevBuf r_o[2], r_d[2], r_f[2], r_t[2];         /* rtx_trace_rays: two sets of chunk buffers, kept between calls */
+	cudaStream_t r_in = nullptr, r_out = nullptr;
+	cudaEvent_t r_ev_in[2] = {}, r_ev_done[2] = {}, r_ev_out[2] = {}, r_ev_a = nullptr, r_ev_b = nullptr;
 	uint32_t build_levels = 0;
 	double build_ms = 0.0;
 	bool tree_on_device = false;                   /* d_ref_* / t_faces / d_triangles hold a complete reference tree */
@@ -572,6 +575,16 @@ void rtx_destroy(rtx_ctx *c)
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	for (cudaEvent_t e : c->band_ev) if (e) cudaEventDestroy(e);
+	for (int k = 0; k < 2; ++k) {
+		c->r_o[k].release(); c->r_d[k].release(); c->r_f[k].release(); c->r_t[k].release();
+		if (c->r_ev_in[k]) cudaEventDestroy(c->r_ev_in[k]);
+		if (c->r_ev_done[k]) cudaEventDestroy(c->r_ev_done[k]);
+		if (c->r_ev_out[k]) cudaEventDestroy(c->r_ev_out[k]);
+	}
+	if (c->r_ev_a) cudaEventDestroy(c->r_ev_a);
+	if (c->r_ev_b) cudaEventDestroy(c->r_ev_b);
+	if (c->r_in) cudaStreamDestroy(c->r_in);
+	if (c->r_out) cudaStreamDestroy(c->r_out);
 	if (c->copy_done) cudaEventDestroy(c->copy_done);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -1295,6 +1308,10 @@ int rtx_trace_rays_device(rtx_ctx *c, const void *d_origins, const void *d_dirs,
 	return RTX_OK;
 }
 
+/* Host arrays in, host arrays out.  Batches larger than one chunk are pipelined over three streams with two sets
+ * of device buffers: while chunk k is traced, chunk k+1 is on its way up and chunk k-1 on its way down, so a big
+ * batch costs about its longest stage (the 32 B/ray upload at PCIe rates) instead of the sum of the three. */
+#define RTX_RAY_CHUNK (4u << 20)
 int rtx_trace_rays(rtx_ctx *c, const float *origins, const float *dirs, size_t nrays, float max_distance,
                    uint32_t *face_id, float *distance)
 {
@@ -1303,29 +1320,64 @@ int rtx_trace_rays(rtx_ctx *c, const float *origins, const float *dirs, size_t n
 	if (nrays == 0) return RTX_OK;
 	if (!origins || !dirs) return fail(c, RTX_ERR_ARG, "null ray arrays");
 	CU(c, cudaSetDevice(c->device));
-	DevBuf d_o, d_d, d_f, d_t;
-	auto cleanup = [&] { d_o.release(); d_d.release(); d_f.release(); d_t.release(); };
+	const size_t chunk = nrays < RTX_RAY_CHUNK ? nrays : RTX_RAY_CHUNK;
+	const size_t nchunks = (nrays + chunk - 1) / chunk;
+	const int nbuf = nchunks > 1 ? 2 : 1;
+	DevBuf *d_o = c->r_o, *d_d = c->r_d, *d_f = c->r_f, *d_t = c->r_t;
+	cudaEvent_t *ev_in = c->r_ev_in, *ev_done = c->r_ev_done, *ev_out = c->r_ev_out;
+	auto cleanup = [&] {};                                  /* buffers, streams and events stay with the context */
+	cudaError_t e = cudaSuccess;
+	auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+	for (int k = 0; k < nbuf; ++k) {
+		ok(d_o[k].alloc(chunk * 16)); ok(d_d[k].alloc(chunk * 16)); ok(d_f[k].alloc(chunk * 4)); ok(d_t[k].alloc(chunk * 4));
+		if (!ev_in[k]) ok(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+		if (!ev_done[k]) ok(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+		if (!ev_out[k]) ok(cudaEventCreateWithFlags(&ev_out[k], cudaEventDisableTiming));
+	}
+	if (!c->r_ev_a) ok(cudaEventCreate(&c->r_ev_a));
+	if (!c->r_ev_b) ok(cudaEventCreate(&c->r_ev_b));
+	if (nchunks > 1) {
+		if (!c->r_in) ok(cudaStreamCreateWithFlags(&c->r_in, cudaStreamNonBlocking));
+		if (!c->r_out) ok(cudaStreamCreateWithFlags(&c->r_out, cudaStreamNonBlocking));
+	}
+	if (e != cudaSuccess) return cuda_fail(c, e, "rtx_trace_rays: buffers / streams");
+	cudaStream_t s_in = c->r_in, s_out = c->r_out;
+	cudaEvent_t ev_a = c->r_ev_a, ev_b = c->r_ev_b;
+	cudaStream_t up = nchunks > 1 ? s_in : c->stream, down = nchunks > 1 ? s_out : c->stream;
 	int rc = RTX_OK;
-	cudaError_t e;
-	if ((e = d_o.alloc(nrays * 16)) != cudaSuccess || (e = d_d.alloc(nrays * 16)) != cudaSuccess ||
-	    (e = d_f.alloc(nrays * 4)) != cudaSuccess || (e = d_t.alloc(nrays * 4)) != cudaSuccess) {
-		cleanup();
-		return cuda_fail(c, e, "cudaMalloc(rays)");
+	ok(cudaEventRecord(ev_a, c->stream));
+	for (size_t k = 0; k < nchunks && rc == RTX_OK && e == cudaSuccess; ++k) {
+		const int b = (int)(k & 1);
+		const size_t first = k * chunk, n = nrays - first < chunk ? nrays - first : chunk;
+		if (k >= 2) ok(cudaStreamWaitEvent(up, ev_done[b], 0));                     /* chunk k-2 no longer reads these inputs */
+		ok(cudaMemcpyAsync(d_o[b].p, origins + 4 * first, n * 16, cudaMemcpyHostToDevice, up));
+		ok(cudaMemcpyAsync(d_d[b].p, dirs + 4 * first, n * 16, cudaMemcpyHostToDevice, up));
+		ok(cudaEventRecord(ev_in[b], up));
+		ok(cudaStreamWaitEvent(c->stream, ev_in[b], 0));
+		if (k >= 2) ok(cudaStreamWaitEvent(c->stream, ev_out[b], 0));               /* chunk k-2's results have left */
+		if (e != cudaSuccess) break;
+		rc = rtx_trace_rays_device(c, d_o[b].p, d_d[b].p, n, max_distance, d_f[b].p, d_t[b].p, c->stream);
+		if (rc != RTX_OK) break;
+		ok(cudaEventRecord(ev_done[b], c->stream));
+		ok(cudaStreamWaitEvent(down, ev_done[b], 0));
+		if (face_id) ok(cudaMemcpyAsync(face_id + first, d_f[b].p, n * 4, cudaMemcpyDeviceToHost, down));
+		if (distance) ok(cudaMemcpyAsync(distance + first, d_t[b].p, n * 4, cudaMemcpyDeviceToHost, down));
+		ok(cudaEventRecord(ev_out[b], down));
 	}
-	if ((e = cudaMemcpyAsync(d_o.p, origins, nrays * 16, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
-	    (e = cudaMemcpyAsync(d_d.p, dirs, nrays * 16, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) {
-		cleanup();
-		return cuda_fail(c, e, "cudaMemcpy(rays)");
-	}
-	rc = rtx_trace_rays_device(c, d_o.p, d_d.p, nrays, max_distance, d_f.p, d_t.p, c->stream);
+	ok(cudaEventRecord(ev_b, c->stream));
+	cudaError_t es = cudaStreamSynchronize(c->stream);
+	if (s_in) { const cudaError_t e2 = cudaStreamSynchronize(s_in); if (es == cudaSuccess) es = e2; }
+	if (s_out) { const cudaError_t e2 = cudaStreamSynchronize(s_out); if (es == cudaSuccess) es = e2; }
+	if (rc == RTX_OK && e != cudaSuccess) rc = cuda_fail(c, e, "rtx_trace_rays");
+	if (rc == RTX_OK && es != cudaSuccess) rc = cuda_fail(c, es, "cudaStreamSynchronize");
 	if (rc == RTX_OK) {
-		if (face_id && (e = cudaMemcpyAsync(face_id, d_f.p, nrays * 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) rc = cuda_fail(c, e, "cudaMemcpy(face_id)");
-		if (rc == RTX_OK && distance && (e = cudaMemcpyAsync(distance, d_t.p, nrays * 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) rc = cuda_fail(c, e, "cudaMemcpy(distance)");
+		rc = finish_stats(c);
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, ev_a, ev_b) == cudaSuccess) c->stats.kernel_ms = ms;   /* the whole pipelined batch on the compute stream */
+		c->stats.rays = nrays;
+		c->stats.kernel_launches = (uint32_t)nchunks;
 	}
-	e = cudaStreamSynchronize(c->stream);
-	if (rc == RTX_OK && e != cudaSuccess) rc = cuda_fail(c, e, "cudaStreamSynchronize");
 	cleanup();
-	if (rc == RTX_OK) rc = finish_stats(c);
 	return rc;
 }
 

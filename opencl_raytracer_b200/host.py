@@ -379,12 +379,15 @@ class CudaHost:
     def bind_output(self, device_ptr: int, count: int):
         self._ck(self._lib.rtx_bind_output(self._ctx, C.c_void_p(device_ptr), count))
 
-    def trace_rays(self, origins, dirs, max_distance: float = 100000.0):
+    def trace_rays(self, origins, dirs, max_distance: float = 100000.0, out_face_id=None, out_distance=None):
+        """Closest hits of host rays (4 floats per origin / direction).  Page-locked inputs AND outputs let the chunks
+        of a large batch overlap their copies with the tracing (rtx_trace_rays)."""
         origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 4)
         dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 4)
         n = origins.shape[0]
-        fid = np.empty(n, np.uint32)
-        dist = np.empty(n, np.float32)
+        fid = out_face_id if out_face_id is not None else np.empty(n, np.uint32)
+        dist = out_distance if out_distance is not None else np.empty(n, np.float32)
+        assert fid.dtype == np.uint32 and dist.dtype == np.float32 and fid.size == n and dist.size == n
         self._ck(self._lib.rtx_trace_rays(self._ctx, origins.ctypes.data, dirs.ctypes.data, n, C.c_float(max_distance),
                                           fid.ctypes.data, dist.ctypes.data))
         return fid, dist

@@ -565,6 +565,30 @@ def test_render_download_pipelined(po, sibenik_scene, soup_scene, frustum, rpt):
         assert np.array_equal(h.render_download(), po.render(soup_scene, 128, 96, 1.0, True, ao=ao).image)
 
 
+def test_trace_rays_pipelined_chunks(po, sibenik_scene):
+    """rtx_trace_rays with more rays than one chunk (4 Mi): upload, tracing and download of consecutive chunks overlap
+    on three streams with two buffer sets; results equal the device-generated batch of the same rays, ray by ray."""
+    import torch
+    host = require_gpu()
+    n = 2 * (4 << 20) + 123457                                     # three chunks, the last one ragged
+    lo, hi = sibenik_scene.root_box()
+    o, d = po.gen_random_rays(1234, 0, n, lo, hi)
+    rt = host.RayTracer(host.Options(width=32, height=32, nSuperSamples=1))
+    with host.CudaHost(rt) as h:
+        h.upload_scene(sibenik_scene)
+        hits, idsum, fid_ref, dist_ref = h.trace_random_rays(1234, 0, n, want_arrays=True)
+        fid, dist = h.trace_rays(o, d)
+        assert h.stats()["kernel_launches"] == 3
+        assert np.array_equal(fid, fid_ref) and np.array_equal(dist, dist_ref)
+        po_, pd_ = torch.from_numpy(o).pin_memory().numpy(), torch.from_numpy(d).pin_memory().numpy()
+        fid2, dist2 = h.trace_rays(po_, pd_, 2.5)                  # pinned inputs (really asynchronous), another max_distance
+        ref = po.trace_rays(sibenik_scene, o[:1 << 16], d[:1 << 16], 2.5)
+        assert np.array_equal(fid2[:1 << 16], ref.face_id) and np.array_equal(dist2[:1 << 16], ref.distance)
+        tail = slice(n - (1 << 14), n)
+        ref = po.trace_rays(sibenik_scene, o[tail], d[tail], 2.5)
+        assert np.array_equal(fid2[tail], ref.face_id) and np.array_equal(dist2[tail], ref.distance)
+
+
 def test_two_contexts_from_two_host_threads(po, soup_scene, sibenik_scene):
     """A context is not thread-safe, different contexts are independent (include/rtx_b200.h): two host threads, each
     with its own context and scene on the same device, upload / render / download concurrently (ctypes releases the
