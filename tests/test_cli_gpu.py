@@ -66,6 +66,28 @@ def test_reference_cli_on_the_bunny_with_default_options(tmp_path, scene_mod, po
     assert np.array_equal(read_pgm(pgm), po.resize(ref.image, 600, 600, 2))
 
 
+@pytest.mark.gpu
+def test_python_cli_mirror_writes_the_same_pgm(tmp_path, scene_mod, soup_golden, ao_golden):
+    """`python -m opencl_raytracer_b200.render`: the reference's options and defaults for hosts without the reference
+    tree; same bytes as the golden PGM payloads of the reference kernel text, with the tree from the host builder and
+    from the device builder; `-m random` works here (the reference's own parser crashes on it)."""
+    require_gpu()
+    import sys
+    g, a = soup_golden, ao_golden
+    off, pgm = str(tmp_path / "soup.off"), str(tmp_path / "out.pgm")
+    scene_mod.write_off(off, g["verts"], g["faces"])
+    base = [sys.executable, "-m", "opencl_raytracer_b200.render"]
+    size = ["-w", str(int(a["width"])), "-h", str(int(a["height"])), "-s", str(int(a["nss"]))]
+    cases = [(["-a", "0", "-f", "1.2345678", "-w", str(int(g["width"])), "-h", str(int(g["height"])), "-s", str(int(g["nss"]))], g["u8"]),
+             (size, a["u8_uniform3"]), (size + ["-m", "random"], a["u8_random3"]),
+             (size + ["-m", "random", "-a", "1", "-d", "1.5", "--device-build"], a["u8_random1_far"]),
+             (size + ["-a", "2", "-d", "0.7", "--device-build"], a["u8_uniform2_d07"])]
+    for extra, want in cases:
+        res = subprocess.run(base + extra + [off, pgm], capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert np.array_equal(read_pgm(pgm), want), extra
+
+
 def test_reference_cli_fails_loudly_without_a_device(tmp_path, scene_mod, soup_golden):
     from opencl_raytracer_b200 import host
     if host.device_count() > 0:
