@@ -869,7 +869,7 @@ int rtx_upload_mesh(rtx_ctx *c, const float *verts16, size_t nverts, const uint3
 		/* the host looks at the live-segment count every 4th level only: a level without live segments is a no-op
 		 * (every kernel returns at once), a round trip to the host costs as much as a level of a small mesh */
 		const bool look = (levels & 3u) == 0 || N < 4096 || N > (1u << 20);      /* a wasted level of a big mesh costs more than the round trip */
-		k_bvh_accumulate<<<grid, 256, 0, st>>>(ids[cur], seg[cur], N, tc, tlo, thi, acc[cur]);
+		k_bvh_accumulate<<<(N + 256 * RTX_BVH_ACC_ITEMS - 1) / (256 * RTX_BVH_ACC_ITEMS), 256, 0, st>>>(ids[cur], seg[cur], N, tc, tlo, thi, acc[cur]);
 		k_bvh_split<<<grid, 256, 0, st>>>(seg[cur], N, acc[cur], c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>());
 		k_bvh_flag_partials<<<nblocks, RTX_BVH_BLOCK, 0, st>>>(ids[cur], seg[cur], acc[cur], tc, N, partials);
 		k_bvh_spine<<<1, 32, 0, st>>>(partials, nblocks);

@@ -59,40 +59,94 @@ __global__ void k_bvh_prepare(const uint32_t *__restrict__ faces, const float4 *
 	}
 }
 
-__global__ void k_bvh_accumulate(const uint32_t *__restrict__ ids, const BvhSeg *__restrict__ seg, uint32_t ntris,
-                                 const float *__restrict__ tc, const float *__restrict__ tlo, const float *__restrict__ thi,
-                                 uint32_t *__restrict__ acc)
+#define RTX_BVH_ACC_ITEMS 8      /* consecutive ids per thread in k_bvh_accumulate */
+
+RTX_DEV void bvh_acc_flush(uint32_t *__restrict__ acc, uint32_t start, const uint32_t (&v)[RTX_BVH_ACC])
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	BvhSeg s = BvhSeg{ 0xffffffffu, 0u, 0u };
-	if (i < ntris) s = seg[i];
-	const bool act = s.n > 1;
-	uint32_t v[RTX_BVH_ACC];
-#pragma unroll
-	for (int k = 0; k < RTX_BVH_ACC; ++k) v[k] = (k % 6) < 3 ? 0xffffffffu : 0u;       /* neutral for min / max */
-	if (act) {
-		const size_t t = ids[i];
-#pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			v[k] = f2ord(tlo[3 * t + k]);
-			v[3 + k] = f2ord(thi[3 * t + k]);
-			v[6 + k] = v[9 + k] = f2ord(tc[3 * t + k]);
-		}
-	}
-	const uint32_t s0 = __shfl_sync(0xffffffffu, s.start, 0);
-	if (__all_sync(0xffffffffu, act && s.start == s0)) {                     /* the whole warp in one segment */
-#pragma unroll
-		for (int k = 0; k < RTX_BVH_ACC; ++k)
-			v[k] = (k % 6) < 3 ? __reduce_min_sync(0xffffffffu, v[k]) : __reduce_max_sync(0xffffffffu, v[k]);
-		if ((threadIdx.x & 31u) != 0) return;
-	} else if (!act) {
-		return;
-	}
-	uint32_t *a = acc + (size_t)s.start * RTX_BVH_ACC;
+	uint32_t *a = acc + (size_t)start * RTX_BVH_ACC;
 #pragma unroll
 	for (int k = 0; k < RTX_BVH_ACC; ++k) {
 		if ((k % 6) < 3) atomicMin(a + k, v[k]); else atomicMax(a + k, v[k]);
 	}
+}
+
+/* Every thread folds RTX_BVH_ACC_ITEMS consecutive ids: runs of one segment are reduced in registers and only a run
+ * that ends inside the thread goes to memory at once; the thread's LAST run is then merged with the neighbouring
+ * lanes' (segments are contiguous, so equal keys are adjacent lanes): one REDUX per quantity when the whole warp sits
+ * in one segment, a segmented shuffle reduction otherwise, and only the first lane of each run issues the atomics.
+ * The top levels (a few huge segments) thus cost N / 256 atomics per address instead of N. */
+__global__ void k_bvh_accumulate(const uint32_t *__restrict__ ids, const BvhSeg *__restrict__ seg, uint32_t ntris,
+                                 const float *__restrict__ tc, const float *__restrict__ tlo, const float *__restrict__ thi,
+                                 uint32_t *__restrict__ acc)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * RTX_BVH_ACC_ITEMS;
+	uint32_t v[RTX_BVH_ACC];
+#pragma unroll
+	for (int k = 0; k < RTX_BVH_ACC; ++k) v[k] = (k % 6) < 3 ? 0xffffffffu : 0u;       /* neutral for min / max */
+	uint32_t cur = 0xffffffffu;                                                   /* segment of the run being folded */
+	for (uint32_t j0 = 0; j0 < RTX_BVH_ACC_ITEMS; j0 += 4) {
+		/* four ids at a time: all their loads are issued before the first is folded (the per-triangle data is a
+		 * random access, and a thread that waits for one element at a time is bound by that latency) */
+		BvhSeg sg[4];
+		uint32_t e[4][9];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const size_t i = base + j0 + j;
+			sg[j] = i < ntris ? seg[i] : BvhSeg{ 0u, 0u, 0u };
+		}
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			if (sg[j].n <= 1) continue;
+			const size_t t = ids[base + j0 + j];
+#pragma unroll
+			for (int k = 0; k < 3; ++k) {
+				e[j][k] = f2ord(tlo[3 * t + k]);
+				e[j][3 + k] = f2ord(thi[3 * t + k]);
+				e[j][6 + k] = f2ord(tc[3 * t + k]);
+			}
+		}
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			if (sg[j].n <= 1) continue;
+			if (cur != 0xffffffffu && sg[j].start != cur) {                           /* a run ended inside this thread */
+				bvh_acc_flush(acc, cur, v);
+#pragma unroll
+				for (int k = 0; k < RTX_BVH_ACC; ++k) v[k] = (k % 6) < 3 ? 0xffffffffu : 0u;
+			}
+			cur = sg[j].start;
+#pragma unroll
+			for (int k = 0; k < 3; ++k) {
+				v[k] = min(v[k], e[j][k]);
+				v[3 + k] = max(v[3 + k], e[j][3 + k]);
+				v[6 + k] = min(v[6 + k], e[j][6 + k]);
+				v[9 + k] = max(v[9 + k], e[j][6 + k]);
+			}
+		}
+	}
+	const bool act = cur != 0xffffffffu;
+	const uint32_t s0 = __shfl_sync(0xffffffffu, cur, 0);
+	if (__all_sync(0xffffffffu, act && cur == s0)) {                              /* the whole warp in one segment */
+#pragma unroll
+		for (int k = 0; k < RTX_BVH_ACC; ++k)
+			v[k] = (k % 6) < 3 ? __reduce_min_sync(0xffffffffu, v[k]) : __reduce_max_sync(0xffffffffu, v[k]);
+		if (lane != 0) return;
+	} else {
+		const uint32_t key = act ? cur : 0xfffffffeu - lane;                      /* idle lanes: runs of their own */
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t k2 = __shfl_down_sync(0xffffffffu, key, o);
+			const bool same = lane + o < 32u && k2 == key;
+#pragma unroll
+			for (int k = 0; k < RTX_BVH_ACC; ++k) {
+				const uint32_t u = __shfl_down_sync(0xffffffffu, v[k], o);
+				if (same) v[k] = (k % 6) < 3 ? min(v[k], u) : max(v[k], u);
+			}
+		}
+		const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+		if (!act || (lane != 0 && prev == key)) return;                           /* only run heads continue */
+	}
+	bvh_acc_flush(acc, cur, v);
 }
 
 /* the first position of every live segment: node record + split plane; acc[0..2] <- (axis, cut, lo) */
