@@ -65,3 +65,18 @@ def test_argument_errors_need_no_device():
     rt = host.RayTracer(host.Options(width=1920, height=1080, nSuperSamples=4))
     assert (rt.totalWidth, rt.totalHeight) == (3840, 2160)
     assert host.RayTracer(host.Options(width=10, height=10, nSuperSamples=8)).totalWidth == 20   # (unsigned)sqrt(8) = 2
+
+
+def test_python_cli_mirror_defaults_match_render_cc():
+    """opencl_raytracer_b200.render mirrors src/render.cc:16-47: same option letters, same defaults
+    { 600, 600, 1.f, 4, shading, AO on, .2f, 3, UNIFORM, 4, 90, LONGEST }; -h is the height, --help the help."""
+    from opencl_raytracer_b200 import render
+    a = render.parse(["in.off", "out.pgm"])
+    assert (a.width, a.height, a.focal_length, a.supersamples) == (600, 600, 1.0, 4)
+    assert (a.ambient_occlusion_samples, a.ambient_occlusion_max_distance, a.ambient_occlusion_method) == (3, 0.2, "uniform")
+    assert a.bvh_strategy == "longest" and a.input_mesh == "in.off" and a.output_image == "out.pgm"
+    a = render.parse(["-w", "32", "-h", "24", "-a", "0", "-d", "1.5", "-m", "random", "-f", "2.5", "-s", "16", "a", "b"])
+    assert (a.width, a.height, a.ambient_occlusion_samples, a.ambient_occlusion_max_distance) == (32, 24, 0, 1.5)
+    assert (a.ambient_occlusion_method, a.focal_length, a.supersamples) == ("random", 2.5, 16)
+    a = render.parse(["--width=7", "--height=9", "--ambient-occlusion-samples=2", "--supersamples=9", "a", "b"])
+    assert (a.width, a.height, a.ambient_occlusion_samples, a.supersamples) == (7, 9, 2, 9)
