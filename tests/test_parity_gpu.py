@@ -651,3 +651,40 @@ def test_second_device_if_present(po, soup_scene):
     finally:
         for h in hosts:
             h.close()
+
+
+def test_remaining_abi_entry_points(po, soup_scene, capfd):
+    """The C-ABI calls no other test touches: rtx_print_info / rtx_device_info, rtx_render_async + rtx_synchronize on a
+    caller stream, rtx_trace_rays_device with torch-owned ray and result buffers, rtx_probe_bandwidth."""
+    import torch
+    host = require_gpu()
+    assert host.CudaHost.printInfo() == 0
+    assert "Hardware information" in capfd.readouterr().out
+    info = host.device_info(0)
+    assert info.cc_major >= 10 and info.sm_count > 0 and info.global_mem_bytes > (1 << 30) and info.l2_bytes > 0
+    rt = host.RayTracer(host.Options(width=96, height=64, nSuperSamples=4))
+    ref = po.render(soup_scene, rt.totalWidth, rt.totalHeight, 1.0, True).image
+    with host.CudaHost(rt) as h:
+        h.upload_scene(soup_scene)
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            h.render_async(stream.cuda_stream)
+            h.resize_u8_async(0, 0, stream.cuda_stream)
+        h.synchronize()
+        assert np.array_equal(h.download(), ref)
+        assert np.array_equal(h.download_u8(), po.resize(ref, rt.options.width, rt.options.height, rt.n))
+        ptr, count = h.device_image()
+        assert ptr != 0 and count == rt.totalWidth * rt.totalHeight
+        lo, hi = soup_scene.root_box()
+        n = 50000
+        o, d = po.gen_random_rays(7, 0, n, lo, hi)
+        want = po.trace_rays(soup_scene, o, d, 100000.0)
+        d_o, d_d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+        d_f = torch.empty(n, dtype=torch.int32, device="cuda")
+        d_t = torch.empty(n, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        h.trace_rays_device(d_o.data_ptr(), d_d.data_ptr(), n, 100000.0, d_f.data_ptr(), d_t.data_ptr(), 0)
+        h.synchronize()
+        assert np.array_equal(d_f.cpu().numpy().view(np.uint32), want.face_id) and np.array_equal(d_t.cpu().numpy(), want.distance)
+        assert h.probe_bandwidth(0, 8 << 20, 4) > 1000.0          # GB/s out of L2
+        assert h.probe_bandwidth(1, 8 << 20, 4) > 1000.0          # GB/s out of L1
