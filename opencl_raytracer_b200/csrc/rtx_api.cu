@@ -82,6 +82,7 @@ struct rtx_ctx {
 	DevBuf d_pairs, d_tris, d_leafbox, d_tnormals, d_ref_nodes, d_ref_aabbs;
 	DevBuf t_faces, t_verts, t_vnormals, t_scan;   /* upload staging, kept between uploads */
 	DevBuf t_build, d_triangles;                   /* rtx_upload_mesh: builder work space; leaf order -> input face id */
+	DevBuf t_parent;                               /* device flatten: parent link of every node pair (k_slack_leaves) */
 	DevBuf r_o[2], r_d[2], r_f[2], r_t[2];         /* rtx_trace_rays: two sets of chunk buffers, kept between calls */
 	cudaStream_t r_in = nullptr, r_out = nullptr;
 	cudaEvent_t r_ev_in[2] = {}, r_ev_done[2] = {}, r_ev_out[2] = {}, r_ev_a = nullptr, r_ev_b = nullptr;
@@ -568,7 +569,7 @@ void rtx_destroy(rtx_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
-	DevBuf *bufs[] = { &c->t_build, &c->d_triangles, &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
+	DevBuf *bufs[] = { &c->t_parent, &c->t_build, &c->d_triangles, &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
 	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists, &c->d_slists, &c->d_raytab,
 	                   &c->d_hit_st, &c->d_ao_ring };
 	for (DevBuf *b : bufs) b->release();
@@ -652,6 +653,7 @@ static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nver
 		int *delta = reinterpret_cast<int *>(pair_idx + n), *partials = delta + n;
 		TreeResult *res = reinterpret_cast<TreeResult *>(partials + (size_t)3 * nblocks);
 		CUU(c->d_pairs.alloc(4 * pair_stride * 64));
+		CUU(c->t_parent.alloc(pair_stride * 4));
 		c->h_tree = TreeResult{ 0xffffffffu, 0u, n == 1 ? 1u : 0u, n == 1 ? 1u : 0u };
 		CUU(cudaMemcpyAsync(res, &c->h_tree, sizeof(TreeResult), cudaMemcpyHostToDevice, st));
 		if (n > 1) {
@@ -666,7 +668,8 @@ static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nver
 		k_flatten_nodes<<<(unsigned)((nnodes + 255) / 256), 256, 0, st>>>(
 			c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>(), first_leaf, pair_idx,
 			c->t_faces.as<uint32_t>(), c->t_verts.as<float4>(), c->t_vnormals.as<float4>(), n, (uint32_t)pair_stride, K,
-			c->d_pairs.as<float4>(), c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>(), (uint32_t)nverts, res);
+			c->d_pairs.as<float4>(), c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>(), (uint32_t)nverts, res,
+			c->t_parent.as<uint32_t>());
 		CUU(cudaGetLastError());
 		CUU(cudaMemcpyAsync(&c->h_tree, res, sizeof(TreeResult), cudaMemcpyDeviceToHost, st));
 		CUU(cudaStreamSynchronize(st));
@@ -712,19 +715,27 @@ static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nver
 	{
 		/* culling slack of the leaves from the conditioning of their triangles (box_slack); ill-shaped triangles
 		 * are rare, and only then is the slack pushed up the tree, one level per pass */
-		unsigned int *fat = c->d_counter.as<unsigned int>() + 2;
-		CUU(cudaMemsetAsync(fat, 0, sizeof(unsigned int), st));
 		const unsigned grid = (unsigned)((num_pairs + 255) / 256);
-		k_slack_leaves<<<grid, 256, 0, st>>>(c->d_pairs.as<float4>(), c->d_tris.as<float4>(), (uint32_t)num_pairs, (uint32_t)pair_stride, fat);
-		CUU(cudaGetLastError());
-		unsigned int h_fat = 0;
-		CUU(cudaMemcpyAsync(&h_fat, fat, sizeof h_fat, cudaMemcpyDeviceToHost, st));
-		CUU(cudaStreamSynchronize(st));
-		if (h_fat) {
-			for (uint32_t pass = 0; pass < depth; ++pass)
-				k_slack_relax<<<grid, 256, 0, st>>>(c->d_pairs.as<float4>(), (uint32_t)num_pairs, (uint32_t)pair_stride);
+		if (device_flatten) {
+			/* parent links from the flatten: every fat leaf raises its ancestors itself, one launch, no round trip */
+			k_slack_leaves<<<grid, 256, 0, st>>>(c->d_pairs.as<float4>(), c->d_tris.as<float4>(), (uint32_t)num_pairs, (uint32_t)pair_stride,
+			                                      c->t_parent.as<uint32_t>(), nullptr);
 			CUU(cudaGetLastError());
 			CUU(cudaStreamSynchronize(st));
+		} else {
+			unsigned int *fat = c->d_counter.as<unsigned int>() + 2;
+			CUU(cudaMemsetAsync(fat, 0, sizeof(unsigned int), st));
+			k_slack_leaves<<<grid, 256, 0, st>>>(c->d_pairs.as<float4>(), c->d_tris.as<float4>(), (uint32_t)num_pairs, (uint32_t)pair_stride, nullptr, fat);
+			CUU(cudaGetLastError());
+			unsigned int h_fat = 0;
+			CUU(cudaMemcpyAsync(&h_fat, fat, sizeof h_fat, cudaMemcpyDeviceToHost, st));
+			CUU(cudaStreamSynchronize(st));
+			if (h_fat) {                 /* no parent links in the host flatten: one level per pass */
+				for (uint32_t pass = 0; pass < depth; ++pass)
+					k_slack_relax<<<grid, 256, 0, st>>>(c->d_pairs.as<float4>(), (uint32_t)num_pairs, (uint32_t)pair_stride);
+				CUU(cudaGetLastError());
+				CUU(cudaStreamSynchronize(st));
+			}
 		}
 	}
 #undef CUU

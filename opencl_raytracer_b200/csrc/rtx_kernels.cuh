@@ -1511,9 +1511,12 @@ __global__ void k_deinterleave(const float *__restrict__ gathered, uint32_t worl
 
 /* ------------------- device-side pieces of the flatten ------------------- */
 
-/* Leaf slots of the node pairs get the slack of their triangles (tri_slack_rel), in all four octant copies;
- * *fat = 1 if any leaf needs more than the default, so that k_slack_relax has something to propagate. */
-__global__ void k_slack_leaves(float4 *__restrict__ pairs, const float4 *__restrict__ tris, uint32_t num_pairs, uint32_t stride, unsigned int *fat)
+/* Leaf slots of the node pairs get the slack of their triangles (tri_slack_rel), in all four octant copies.  A leaf
+ * that needs more than the default raises every ancestor's slot to its slack: with the parent links of the device
+ * flatten (parent[q] = (pair << 1) | slot that refers to q) right here, by atomicMax on the bits (slacks are >= 0, so
+ * their bit patterns order like the values); without them *fat = 1 tells the host to run k_slack_relax. */
+__global__ void k_slack_leaves(float4 *__restrict__ pairs, const float4 *__restrict__ tris, uint32_t num_pairs, uint32_t stride,
+                               const uint32_t *__restrict__ parent, unsigned int *fat)
 {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= num_pairs) return;
@@ -1527,7 +1530,16 @@ __global__ void k_slack_leaves(float4 *__restrict__ pairs, const float4 *__restr
 		if (rel == RTX_SLACK_REL) continue;
 		const float slack = box_slack_rel(a.x, a.y, a.z, a.w, b.x, b.y, rel);      /* copy 0 is unswapped: (lo.xyz, hi.x), (hi.y, hi.z) */
 		for (int v = 0; v < 4; ++v) pairs[((size_t)v * stride + p) * 4 + 2 * k + 1].w = slack;
-		*fat = 1u;
+		if (!parent) { *fat = 1u; continue; }
+		const unsigned int bits = __float_as_uint(slack);
+		for (uint32_t q = p; q != 0;) {
+			const uint32_t e = parent[q], pp = e >> 1, slot = e & 1u;
+			unsigned int *w0 = reinterpret_cast<unsigned int *>(&pairs[(size_t)pp * 4 + 2 * slot + 1].w);
+			if (*reinterpret_cast<volatile unsigned int *>(w0) >= bits) break;      /* whoever raised it carries on upwards */
+			for (int v = 0; v < 4; ++v)
+				atomicMax(reinterpret_cast<unsigned int *>(&pairs[((size_t)v * stride + pp) * 4 + 2 * slot + 1].w), bits);
+			q = pp;
+		}
 	}
 }
 
@@ -1695,7 +1707,7 @@ __global__ void k_flatten_nodes(const uint32_t *__restrict__ nodes, const float4
                                 const uint32_t *__restrict__ faces, const float4 *__restrict__ verts,
                                 const float4 *__restrict__ vnormals, uint32_t nnodes, uint32_t num_pairs, uint32_t leaf_size,
                                 float4 *__restrict__ pairs, float4 *__restrict__ tris, float4 *__restrict__ leafbox,
-                                float4 *__restrict__ tnormals, uint32_t nverts, TreeResult *res)
+                                float4 *__restrict__ tnormals, uint32_t nverts, TreeResult *res, uint32_t *__restrict__ parent)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nnodes) return;
@@ -1752,6 +1764,7 @@ __global__ void k_flatten_nodes(const uint32_t *__restrict__ nodes, const float4
 		const uint32_t c = child[k];
 		const uint32_t clv = (nodes[c] + 1) >> 1;
 		const int ref = clv > leaf_size ? (int)pair_idx[c] : (int)~((first_leaf[c] << 3) | (clv - 1));
+		if (ref >= 0 && parent) parent[ref] = (p << 1) | (uint32_t)k;           /* for k_slack_leaves */
 		const float4 lo = ref_aabbs[2 * (size_t)c], hi = ref_aabbs[2 * (size_t)c + 1];
 		a[k] = make_float4(lo.x, lo.y, lo.z, hi.x);
 		b[k] = make_float4(hi.y, hi.z, __int_as_float(ref), box_slack(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z));
