@@ -180,3 +180,16 @@ def test_port_on_the_reference_sah_tree(po, sah_scene, sah_golden, soup_scene):
     # same triangles, other leaf order: same picture wherever no two triangles tie
     plain = po.render(soup_scene, 64, 48, 1.0, True)
     assert (r.distance == plain.distance).mean() > 0.999
+
+
+def test_ambient_occlusion_bunny_defaults_against_reference_library(po, bunny_scene):
+    """`./render bunny.off out.pgm` with no options (uniform AO, 3 rings, 0.2): restatement == the reference's kernel
+    text on a 300x300 frame of the reference's own mesh (thousands of candidate leaves within reach of a surface point)."""
+    if po.ref() is None:
+        pytest.skip("oracle/_ref/libref_oracle.so not present")
+    ao = po.Ao.make()
+    r = po.render(bunny_scene, 300, 300, 1.0, True, ao=ao)
+    img = po.ref_render_ao(bunny_scene, 300, 300, ao)
+    assert np.array_equal(_bits(r.image), _bits(img))
+    plain = po.render(bunny_scene, 300, 300, 1.0, True)
+    assert (r.image < plain.image).mean() > 0.1
