@@ -20,6 +20,8 @@ from oracle import pyoracle as po  # noqa: E402
 def make_mesh(rng):
     kind = rng.integers(0, 8)
     n = int(rng.choice([30, 200, 1000, 4000]))
+    if os.environ.get("FUZZ_BIG"):                         # deeper trees: FUZZ_BIG=30000 python tools/fuzz_gpu.py ...
+        n = int(os.environ["FUZZ_BIG"])
     if kind == 0:        # plain soup
         v, f = scenes.random_soup(n, seed=int(rng.integers(1 << 30)), size=float(rng.choice([0.05, 0.35, 1.0])))
         return v.astype(np.float64), f, "soup"
