@@ -125,3 +125,23 @@ def test_ao_tile_partition(po, soup_scene, world):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_ao_on_a_tree_deeper_than_the_stack(po, scene_mod):
+    """100 coincident triangles build a chain deeper than the 64-entry traversal stack (bvh.cc:85-93): primary rays and
+    occlusion rays both take the literal stackless walk (walk_reference / walk_reference_any)."""
+    host = require_gpu()
+    from opencl_raytracer_b200 import scenes
+    v1, _ = scenes.random_soup(1, seed=3, extent=0.5, size=2.0, big=0)
+    vs, fs = scenes.random_soup(60, seed=8, size=0.5)
+    v = np.concatenate([np.tile(v1, (100, 1)), vs])
+    f = np.concatenate([np.arange(300, dtype=np.uint32).reshape(-1, 3), fs.astype(np.uint32) + 300])
+    sc = scene_mod.scene_from_mesh(v, f, name="chain+soup")
+    for ao in (po.Ao.make(method=0, samples=2, max_distance=0.8), po.Ao.make(method=1, samples=3, max_distance=0.8)):
+        rt = host.RayTracer(_options(host, 96, 64, 4, ao))
+        with host.CudaHost(rt) as h:
+            h.upload_scene(sc)
+            h()
+            st = h.stats()
+            assert st["tree_depth"] > 64 and st["kernel_variant"] == host.KERNEL_EXHAUSTIVE
+            _compare(host, po, sc, rt, h, ao)
