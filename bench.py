@@ -613,6 +613,15 @@ def main():
                     "issue": ({"issue_active_pct": prof.get("issue_active_pct"), "warp_instructions": prof.get("warp_instructions"),
                                "avg_threads_per_instruction": prof.get("avg_threads_per_instruction"),
                                "source": "ncu --set full, profiles/r1_c3_final_ncu.txt"} if prof else None)}
+        if prof.get("l1_load_bytes") and kernel_s > 0 and world == 1:
+            # bytes per launch from the ncu capture (fixed for the workload) over the kernel time measured in this run
+            frac_list = prof.get("share_of_kernel_ms_pct", 100.0) / 100.0
+            roofline["measured_traffic"] = {
+                "l1_load_GBps": prof["l1_load_bytes"] / (kernel_s * frac_list) / 1e9, "l1_hit_pct": prof.get("l1_hit_pct"),
+                "l2_read_GBps": prof["l2_read_bytes_from_l1"] / (kernel_s * frac_list) / 1e9, "l2_hit_pct": prof.get("l2_hit_pct"),
+                "l2_frac_of_probed_peak": prof["l2_read_bytes_from_l1"] / (kernel_s * frac_list) / 1e9 / l2_peak,
+                "hbm_GBps": traffic / (kernel_s * frac_list) / 1e9 if traffic else None,
+                "source": "l1tex__t_sectors_pipe_lsu_mem_global_op_ld, lts__t_sectors_srcunit_tex_op_read, dram__bytes_* (%s)" % prof.get("source", "profiles/")}
         if prof.get("warp_instructions") and prof.get("duration_ms") and clocks.get("sm_mhz"):
             # the bound that actually holds: warp instructions issued per second against 4 schedulers x 1 instruction
             # per clock per SM.  Instruction count from the ncu capture of this kernel (fixed for the workload),
