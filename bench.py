@@ -51,6 +51,21 @@ METRIC = {"c3": "Mrays/s closest-hit (sibenik, 4K)", "c2": "Mrays/s closest-hit 
           "c1": "Mrays/s closest-hit (bunny, reference defaults)", "c4": "Mrays/s closest-hit (bunny x144, 4K)"}
 
 
+CPU_ROW_STEP = 16      # both CPU legs time every 16th row of the frame (rows 8, 24, ...): fixed, so both arms can state it
+
+
+def make_config(desc, scene_name, ntris, tw, th, world, gather):
+    """The `config` object, identical in the GPU arm and in --impl reference (the driver compares the two)."""
+    nrows = len(range(CPU_ROW_STEP // 2, th, CPU_ROW_STEP))
+    return {"workload": desc, "scene": scene_name, "triangles": int(ntris), "rays_per_step": int(tw * th),
+            "parallelism": "interleaved 32x32 tiles over %d GPU(s), scene replicated, 1 NCCL gather/frame" % world,
+            "step": "trace + RayTracer::resize on the device%s -> %s image on rank 0" % (
+                " + 1 NCCL gather + de-interleave" if world > 1 else "", "byte" if gather == "u8" else "float"),
+            "l2": "flushed between timed iterations (256 MiB memset, untimed)",
+            "reference_arm_sample": "the CPU arm (--impl reference, cpu_baseline) times every %d-th row of the same %dx%d frame "
+                                    "(%d rows = %.2f M rays per pass) on all host cores" % (CPU_ROW_STEP, tw, th, nrows, nrows * tw / 1e6)}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -59,16 +74,36 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def build_scene(kind):
-    from opencl_raytracer_b200 import scene, scenes
+def mesh_of(kind):
+    """(vertices, faces) of a workload's mesh.  Generators only: no library of this repo is loaded."""
+    from opencl_raytracer_b200 import scenes
     if kind in ("bunny", "bunny_x144"):
         from oracle import pyoracle as po          # only for the staged reference mesh file
         v, f = po.read_mesh_bin(po.staged_bunny_path())
         if kind == "bunny_x144":
             v, f = scenes.subdivided(v, f)
-        return scene.scene_from_mesh(v, f, name=kind)
+        return v, f, kind
     v, f = scenes.sibenik_standin()
-    return scene.scene_from_mesh(v, f, name="sibenik_standin")
+    return v, f, "sibenik_standin"
+
+
+def build_scene(kind):
+    from opencl_raytracer_b200 import scene
+    v, f, name = mesh_of(kind)
+    return scene.scene_from_mesh(v, f, name=name)
+
+
+def build_scene_reference(kind):
+    """The scene of the reference arm: mesh.cc + bvh.cc of the reference itself (oracle/_ref, compiled from
+    /root/reference in the build container), so that arm loads nothing of this repo's product.  Falls back to the
+    host builder of this repo only when oracle/_ref is absent (then cpu_baseline.kind says "port")."""
+    from oracle import pyoracle as po
+    from opencl_raytracer_b200.scene import Scene            # a dataclass; importing it loads no library
+    v, f, name = mesh_of(kind)
+    if po.ref() is None:
+        return build_scene(kind)
+    r = po.ref_scene_from_mesh(v, f)
+    return Scene(r.faces, r.nodes, r.aabbs, r.vertices, r.normals, r.triangles, r.orig_faces, name=name)
 
 
 class ClockSampler(threading.Thread):
@@ -123,22 +158,16 @@ class ClockSampler(threading.Thread):
 
 
 class CpuArm:
-    """The reference CPU path on a bounded row sample of the frame: the reference's own kernel text
-    (oracle/_ref, kind "reference") when it was compiled in the build container, else the C port."""
+    """The reference CPU path on a bounded row sample of the frame (every CPU_ROW_STEP-th row): the reference's own
+    kernel text (oracle/_ref, kind "reference") when it was compiled in the build container, else the C port."""
 
-    def __init__(self, sc, tw, th, budget_s=12.0):
+    def __init__(self, sc, tw, th):
         from oracle import pyoracle as po
         self.po, self.sc, self.tw, self.th = po, sc, tw, th
         self.use_ref = po.ref() is not None
         self.cores = int(po.ref().ref_online_cpus() if self.use_ref else po.port().orc_online_cpus())
-        step = max(1, th // 16)
-        self.rows = (step // 2, th, step)
+        self.rows = (CPU_ROW_STEP // 2, th, CPU_ROW_STEP)
         self.run()                                       # warm-up: page in, start threads
-        dt = self.run()
-        rate = self.nrays / dt
-        want_rows = int(min(th, max(len(range(*self.rows)), rate * budget_s / tw)))
-        step = max(1, th // want_rows)
-        self.rows = (step // 2, th, step)
 
     @property
     def nrays(self):
@@ -152,10 +181,18 @@ class CpuArm:
             self.po.render(self.sc, self.tw, self.th, 1.0, True, rows=self.rows, want_ids=False)
         return time.perf_counter() - t
 
-    def info(self, mrays, dt):
+    def run_for(self, budget_s):
+        """repeat the sample until budget_s of CPU work is done; (passes, seconds)"""
+        n, total = 0, 0.0
+        while n < 1 or total < budget_s:
+            total += self.run()
+            n += 1
+        return n, total
+
+    def info(self, mrays, dt, passes=1):
         return {"value": mrays, "unit": "Mrays/s", "cores": self.cores, "kind": "reference" if self.use_ref else "port",
-                "sample": "every %d-th row of the %dx%d frame (%d rows, %.2fM rays, %.2f s per pass), %d pinned threads"
-                          % (self.rows[2], self.tw, self.th, len(range(*self.rows)), self.nrays / 1e6, dt, self.cores)}
+                "sample": "every %d-th row of the %dx%d frame (%d rows, %.2fM rays, %.2f s per pass, %d pass(es)), %d pinned threads"
+                          % (self.rows[2], self.tw, self.th, len(range(*self.rows)), self.nrays / 1e6, dt, passes, self.cores)}
 
 
 def oracle_counters(sc, tw, th):
@@ -314,28 +351,29 @@ def main():
         return bench_c5(args, rank, world, local_rank, desc)
 
     if args.impl == "reference":
+        # Nothing of this repo's product on this path: no g.build(), no librtx_*.so.  The scene comes from the
+        # reference's own mesh.cc + bvh.cc and the timed loop is the reference's kernel text, both in
+        # oracle/_ref/libref_oracle.so (src/render.cc:76-111 is the sequence being reproduced).
         if rank != 0:
             return 0
-        import __graft_entry__ as g
-        g.build(quiet=True)
-        sc = build_scene(scene_kind)
+        sc = build_scene_reference(scene_kind)
         n = int(np.sqrt(nss))
         tw, th = width * n, height * n
-        arm = CpuArm(sc, tw, th, budget_s=3.0)
+        arm = CpuArm(sc, tw, th)
         times = []
         for i in range(args.warmup + args.steps):
             dt = arm.run()
             if i >= args.warmup:
                 times.append(dt)
         v = arm.nrays * len(times) / sum(times) / 1e6
-        info = arm.info(v, float(np.mean(times)))
-        rays_per_step = arm.nrays
+        info = arm.info(v, float(np.mean(times)), len(times))
         print(json.dumps({
             "impl": "reference", "metric": METRIC.get(args.workload, METRIC["c3"]), "value": v, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": rays_per_step / v / 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "scene": sc.name, "triangles": sc.num_triangles, "parallelism": "host threads"},
+            "config": make_config(desc, sc.name, sc.num_triangles, tw, th, max(1, args.gpus), args.gather),
+            "rays_timed_per_step": arm.nrays,
             "cpu_baseline": info,
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -636,9 +674,9 @@ def main():
                                                      "peak = %d SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the timed region)"
                                                      % (prof.get("source", "profiles/"), prof.get("share_of_kernel_ms_pct", 100.0), sms, clocks["sm_mhz"])}
         if world == 1 and not args.no_cpu:
-            arm = CpuArm(sc, tw, th, budget_s=12.0)
-            dt = arm.run()
-            cpu = arm.info(arm.nrays / dt / 1e6, dt)
+            arm = CpuArm(sc, tw, th)
+            passes, total_s = arm.run_for(10.0)
+            cpu = arm.info(arm.nrays * passes / total_s / 1e6, total_s / passes, passes)
     r.close()
 
     if rank == 0:
@@ -646,11 +684,7 @@ def main():
             "metric": METRIC.get(args.workload, METRIC["c3"]), "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "scene": sc.name, "triangles": sc.num_triangles, "rays_per_step": rays,
-                       "parallelism": "interleaved 32x32 tiles over %d GPU(s), scene replicated, 1 NCCL gather/frame" % world,
-                       "step": "trace + RayTracer::resize on the device%s -> %s image on rank 0" % (
-                           " + 1 NCCL gather + de-interleave" if world > 1 else "", "byte" if args.gather == "u8" else "float"),
-                       "l2": "flushed between timed iterations (256 MiB memset, untimed)"},
+            "config": make_config(desc, sc.name, sc.num_triangles, tw, th, world, args.gather),
             "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(lt.item()),
             "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "other_gather": other, "extras": extras,
             "step_ms": [float(x) for x in step_ms],

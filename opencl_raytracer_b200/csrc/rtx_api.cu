@@ -93,6 +93,7 @@ struct rtx_ctx {
 	TreeResult h_tree{};         /* result words of the device-side tree check (k_tree_*) */
 	f3 bbmin{}, bbmax{};
 	uint32_t tree_depth = 0;
+	bool boxes_nested = true;    /* every child box inside its parent's (k_tree_check); false: literal walk for every ray */
 	/* image */
 	uint32_t W = 0, H = 0, tiles_x = 0, tiles_y = 0, tiles_per_rank = 0, local_tiles = 0;
 	uint32_t rank = 0, world = 1;
@@ -245,24 +246,33 @@ void flatten(const uint32_t *nodes, const float *aabbs16, size_t n, int leaf_siz
 
 /* ------------------------------ launches -------------------------------- */
 
-/* Resident CTAs per SM of a kernel, asked once per (kernel, device, shared-memory size): the query and the
- * shared-memory opt-in cost host time on every launch otherwise. */
+/* Resident CTAs per SM of a kernel, asked once per (kernel, device, shared-memory size): the query costs host time
+ * on every launch otherwise.  Only the occupancy is cached.  The dynamic shared-memory opt-in is a property of the
+ * kernel, not of the cache entry: it is tracked per (kernel, device) and only ever raised, so a launch with a size
+ * that was seen before can never meet an attribute a smaller launch lowered in between. */
 struct OccEntry { const void *kernel; int device; size_t smem; int occ; };
-static OccEntry g_occ[128];
-static int g_nocc = 0;
-static std::mutex g_occ_mutex;     /* contexts on different host threads share the table */
+struct SmemEntry { const void *kernel; int device; size_t max_smem; };
+static std::vector<OccEntry> g_occ;
+static std::vector<SmemEntry> g_smem;
+static std::mutex g_occ_mutex;     /* contexts on different host threads share the tables */
 
 template <typename K>
 cudaError_t resident_blocks(K kernel, int block, size_t smem, int device, int *occ_out)
 {
 	const void *key = reinterpret_cast<const void *>(kernel);
 	std::lock_guard<std::mutex> lock(g_occ_mutex);
-	for (int i = 0; i < g_nocc; ++i)
-		if (g_occ[i].kernel == key && g_occ[i].device == device && g_occ[i].smem == smem) { *occ_out = g_occ[i].occ; return cudaSuccess; }
-	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return e;
+	SmemEntry *se = nullptr;
+	for (SmemEntry &x : g_smem)
+		if (x.kernel == key && x.device == device) { se = &x; break; }
+	if (!se || smem > se->max_smem) {
+		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		if (se) se->max_smem = smem; else g_smem.push_back(SmemEntry{ key, device, smem });
+	}
+	for (const OccEntry &x : g_occ)
+		if (x.kernel == key && x.device == device && x.smem == smem) { *occ_out = x.occ; return cudaSuccess; }
 	int occ = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem);
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem);
 	if (e != cudaSuccess) return e;
 	if (occ < 1) occ = 1;
 	/* the traversal kernels live on L1 hits of node pairs and triangles: ask for the smallest shared-memory
@@ -275,7 +285,7 @@ cudaError_t resident_blocks(K kernel, int block, size_t smem, int device, int *o
 		if (want > 100) want = 100;
 		cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, want);   /* a hint: errors ignored */
 	}
-	if (g_nocc < 128) g_occ[g_nocc++] = OccEntry{ key, device, smem, occ };
+	g_occ.push_back(OccEntry{ key, device, smem, occ });
 	*occ_out = occ;
 	return cudaSuccess;
 }
@@ -513,6 +523,14 @@ int rtx_create(rtx_ctx **out, const rtx_options *options)
 			if (options->ao_alpha_max <= 0 || options->ao_alpha_max > 360)
 				return fail(nullptr, RTX_ERR_ARG, "uniform ambient occlusion needs 0 < alpha_max <= 360 degrees");
 			const double step = (double)options->ao_alpha_max * 3.14159265358979323846 / 180.0 / (double)options->ao_num_samples;
+			/* ray_count = (uint)(2 pi cos(angle) / step) (intersect_kernel.cl:240) must be >= 1 on every ring: at
+			 * angle >= 90 degrees the cosine is <= 0, the conversion of a negative double to uint is undefined in
+			 * OpenCL C as in C, and phi = 0/0 (:243).  The outermost ring has the largest angle. */
+			const double worst = ((double)options->ao_alpha_max * (double)(options->ao_num_samples - 1) / (double)options->ao_num_samples
+			                      + (double)options->ao_alpha_min) * 3.14159265358979323846 / 180.0;
+			if (options->ao_alpha_min < 0 || !(worst < 1.5707) || !(6.2831853071795865 * std::cos(worst) / step >= 1.001))
+				return fail(nullptr, RTX_ERR_ARG, "uniform ambient occlusion: the outermost ring (alpha_max*(samples-1)/samples + alpha_min) "
+				                                  "must stay below 90 degrees and hold at least one ray");
 			ring_cap = (uint64_t)options->ao_num_samples * ((uint64_t)(6.2831853071795865 / step) + 2);
 			if (ring_cap > (1u << 22)) return fail(nullptr, RTX_ERR_ARG, "too many ambient occlusion rings");
 		}
@@ -648,17 +666,17 @@ static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nver
 		const uint32_t K = (uint32_t)c->leaf_size, n = (uint32_t)nnodes;
 		pair_stride = ntris > 1 ? ntris - 1 : 1;                       /* internal nodes of a full binary tree: the bound for any K */
 		const uint32_t per_block = RTX_SCAN_BLOCK * RTX_SCAN_ITEMS, nblocks = (n + per_block - 1) / per_block;
-		CUU(c->t_scan.alloc(((size_t)3 * n + (size_t)3 * nblocks + 4) * 4));
+		CUU(c->t_scan.alloc(((size_t)3 * n + (size_t)3 * nblocks) * 4 + sizeof(TreeResult) + 16));
 		uint32_t *first_leaf = c->t_scan.as<uint32_t>(), *pair_idx = first_leaf + n;
 		int *delta = reinterpret_cast<int *>(pair_idx + n), *partials = delta + n;
 		TreeResult *res = reinterpret_cast<TreeResult *>(partials + (size_t)3 * nblocks);
 		CUU(c->d_pairs.alloc(4 * pair_stride * 64));
 		CUU(c->t_parent.alloc(pair_stride * 4));
-		c->h_tree = TreeResult{ 0xffffffffu, 0u, n == 1 ? 1u : 0u, n == 1 ? 1u : 0u };
+		c->h_tree = TreeResult{ 0xffffffffu, 0u, n == 1 ? 1u : 0u, n == 1 ? 1u : 0u, 0u };
 		CUU(cudaMemcpyAsync(res, &c->h_tree, sizeof(TreeResult), cudaMemcpyHostToDevice, st));
 		if (n > 1) {
 			CUU(cudaMemsetAsync(delta, 0, (size_t)n * 4, st));
-			k_tree_check<<<(n + 255) / 256, 256, 0, st>>>(c->d_ref_nodes.as<uint32_t>(), n, K, delta, res);
+			k_tree_check<<<(n + 255) / 256, 256, 0, st>>>(c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>(), n, K, delta, res);
 			k_tree_partials<<<nblocks, RTX_SCAN_BLOCK, 0, st>>>(c->d_ref_nodes.as<uint32_t>(), delta, n, K, partials);
 			k_tree_spine<<<1, 96, 0, st>>>(partials, nblocks, res);
 			k_tree_scan<<<nblocks, RTX_SCAN_BLOCK, 0, st>>>(c->d_ref_nodes.as<uint32_t>(), delta, n, K, partials, first_leaf, pair_idx, res);
@@ -678,12 +696,23 @@ static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nver
 		if (c->h_tree.bad_face) return fail(c, RTX_ERR_ARG, "face index out of range");
 		num_pairs = c->h_tree.num_pairs;
 		depth = c->h_tree.depth;
+		c->boxes_nested = c->h_tree.loose == 0;
 	} else {
 		/* host flatten (needed for the breadth-first prefix that RTX_TUNE_TOP_SMEM stages in shared memory) */
 		if (!validate_tree(nodes, nnodes, ntris, why)) return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "malformed BVH: " + why);
 		uint32_t bad = 0;                          /* branch-free range check of the vertex indices */
 		for (size_t i = 0; i < nfaceidx; ++i) bad |= (uint32_t)(faces[i] >= nverts);
 		if (bad) return cudaStreamSynchronize(st), fail(c, RTX_ERR_ARG, "face index out of range");
+		c->boxes_nested = true;                    /* same containment check as k_tree_check */
+		for (size_t i = 0; i < nnodes && c->boxes_nested; ++i) {
+			if (nodes[i] == 1) continue;
+			const float *p = aabbs16 + 8 * i;
+			const size_t kids[2] = { i + 1, i + 1 + nodes[i + 1] };
+			for (size_t ch : kids) {
+				const float *q = aabbs16 + 8 * ch;
+				if (!(q[0] >= p[0] && q[1] >= p[1] && q[2] >= p[2] && q[4] <= p[4] && q[5] <= p[5] && q[6] <= p[6])) c->boxes_nested = false;
+			}
+		}
 		Flat flat;
 		flatten(nodes, aabbs16, nnodes, c->leaf_size, c->top_smem > 0 ? (uint32_t)c->top_smem : 0u, flat);
 		const size_t pair_vecs = flat.pairs.size();
@@ -774,6 +803,7 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	if (naabbvec != 2 * nnodes) return fail(c, RTX_ERR_ARG, "aabbs must hold 2 vectors per node");
 	if (nverts != nnormals || nverts == 0) return fail(c, RTX_ERR_ARG, "one normal per vertex required");
 	if (ntris >= (1u << 28)) return fail(c, RTX_ERR_ARG, "too many triangles (limit 2^28)");
+	if (nnodes == 0) return fail(c, RTX_ERR_ARG, "malformed BVH: no nodes");       /* nodes[0] / aabbs16[0..7] are read below */
 	CU(c, cudaSetDevice(c->device));
 	c->uploaded = false;
 	c->tree_on_device = false;
@@ -999,7 +1029,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 	w.face_id = rec ? c->d_face_id.as<uint32_t>() : nullptr;
 	w.dist = rec ? c->d_dist.as<float>() : nullptr;
 	w.hit_st = c->ao ? c->d_hit_st.as<float2>() : nullptr;
-	w.ordered_ok = c->tree_depth <= RTX_STACK_MAX ? 1 : 0;
+	w.ordered_ok = (c->tree_depth <= RTX_STACK_MAX && c->boxes_nested) ? 1 : 0;
 	/* frustum front end pays off when packets see few triangles: many rays per triangle */
 	const double rays_per_tri = (double)c->W * c->H / (double)c->sc.num_tris;
 	w.frustum = (c->frustum == 1 || (c->frustum < 0 && rays_per_tri >= 24.0)) && w.ordered_ok ? 1 : 0;
@@ -1305,7 +1335,7 @@ int rtx_trace_rays_device(rtx_ctx *c, const void *d_origins, const void *d_dirs,
 	w.counter = c->d_counter.as<unsigned int>();
 	w.face_id = static_cast<uint32_t *>(d_face_id);
 	w.dist = static_cast<float *>(d_distance);
-	w.ordered_ok = c->tree_depth <= RTX_STACK_MAX ? 1 : 0;
+	w.ordered_ok = (c->tree_depth <= RTX_STACK_MAX && c->boxes_nested) ? 1 : 0;
 	w.exhaustive = c->kernel == RTX_KERNEL_EXHAUSTIVE;
 	CU(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
 	if (c->counters) CU(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(Counters), st));
@@ -1417,7 +1447,7 @@ int rtx_trace_random_rays(rtx_ctx *c, uint32_t seed, uint64_t first, size_t nray
 	w.dist = distance ? c->d_dist.as<float>() : nullptr;
 	w.hit_count = c->d_sums.as<unsigned long long>();
 	w.sum_face_id = c->d_sums.as<unsigned long long>() + 1;
-	w.ordered_ok = c->tree_depth <= RTX_STACK_MAX ? 1 : 0;
+	w.ordered_ok = (c->tree_depth <= RTX_STACK_MAX && c->boxes_nested) ? 1 : 0;
 	w.exhaustive = c->kernel == RTX_KERNEL_EXHAUSTIVE;
 	CU(c, cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned int), st));
 	CU(c, cudaMemsetAsync(c->d_sums.p, 0, 2 * sizeof(unsigned long long), st));

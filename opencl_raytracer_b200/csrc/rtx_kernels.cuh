@@ -262,7 +262,7 @@ RTX_DEV void closest_hit(const SceneDev &sc, const float4 *s_top, uint2 *s_stack
 	best.dist = __int_as_float(0x7f800000);
 	best.tri = 0xffffffffu;
 	best.s = best.t = 0.f;
-	const bool plain = d.x != 0.0f && d.y != 0.0f && d.z != 0.0f;   /* false for NaN too */
+	const bool plain = ray_is_plain(o, d);
 	if (ordered_ok && plain) {
 		if (PRIMARY) {
 			const unsigned mask = __activemask();
@@ -799,7 +799,7 @@ k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 			d[r] = primary_dir(w.cam, x, y);
 			if (ty < w.tiles_y && x < w.cam.W && y < w.cam.H) {
 				valid |= 1u << r;
-				if (d[r].x != 0.0f && d[r].y != 0.0f && d[r].z != 0.0f) {
+				if (ray_is_plain(o, d[r])) {
 					packet |= 1u << r;
 					const int oc = (d[r].x < 0.0f ? 1 : 0) | (d[r].y < 0.0f ? 2 : 0) | (d[r].z < 0.0f ? 0 : 4);
 					if (oct < 0) oct = oc; else same = same && oc == oct;
@@ -1034,7 +1034,7 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 					}
 					if (valid) {
 						r.best.dist = __int_as_float(0x7f800000); r.best.tri = 0xffffffffu; r.best.s = r.best.t = 0.f;
-						const bool plain = r.d.x != 0.0f && r.d.y != 0.0f && r.d.z != 0.0f;
+						const bool plain = ray_is_plain(r.o, r.d);
 						if (ordered_ok && plain) {
 							r.id = make_f3(rn_div(1.0f, r.d.x), rn_div(1.0f, r.d.y), rn_div(1.0f, r.d.z));
 							r.inv_len = rsqrtf(fmaxf(r.d.x * r.d.x + r.d.y * r.d.y + r.d.z * r.d.z, 1e-30f));
@@ -1174,8 +1174,8 @@ struct AoParams {
 RTX_DEV float t_sin(float x) { return (float)sin((double)x); }
 RTX_DEV float t_cos(float x) { return (float)cos((double)x); }
 RTX_DEV float t_acos(float x) { return (float)acos((double)x); }
-RTX_DEV float t_cospi(float x) { return (float)cos((double)rn_mul(3.14159265358979323846f, x)); }
-RTX_DEV float t_sinpi(float x) { return (float)sin((double)rn_mul(3.14159265358979323846f, x)); }
+RTX_DEV float t_cospi(float x) { return (float)cos(__dmul_rn(3.14159265358979323846, (double)x)); }
+RTX_DEV float t_sinpi(float x) { return (float)sin(__dmul_rn(3.14159265358979323846, (double)x)); }
 
 RTX_DEV f3 normalize3(f3 a)
 {
@@ -1255,7 +1255,7 @@ RTX_DEV int ao_entry_pair(const SceneDev &sc, f3 p, float max_distance)
 
 RTX_DEV bool any_hit(const SceneDev &sc, bool ordered_ok, int entry, f3 o, f3 d, float max_distance)
 {
-	const bool plain = d.x != 0.0f && d.y != 0.0f && d.z != 0.0f && d.x == d.x && d.y == d.y && d.z == d.z;
+	const bool plain = ray_is_plain(o, d);
 	if (!(ordered_ok && plain)) return walk_reference_any(sc, o, d, max_distance);
 	if (entry < 0) return false;
 	const f3 id = make_f3(rn_div(1.0f, d.x), rn_div(1.0f, d.y), rn_div(1.0f, d.z));
@@ -1574,6 +1574,7 @@ struct TreeResult {
 	unsigned int bad_face;      /* 1 if a face index is out of range */
 	unsigned int num_pairs;
 	unsigned int depth;
+	unsigned int loose;         /* 1 if some child box is not inside its parent's box (k_tree_check) */
 };
 
 #define RTX_SCAN_ITEMS 16       /* nodes per thread */
@@ -1581,18 +1582,33 @@ struct TreeResult {
 
 RTX_DEV bool tree_is_pair(uint32_t size, uint32_t i, uint32_t leaf_size) { return size > 1 && (((size + 1) >> 1) > leaf_size || i == 0); }
 
-__global__ void k_tree_check(const uint32_t *__restrict__ nodes, uint32_t n, uint32_t leaf_size, int *__restrict__ delta, TreeResult *res)
+/* Also checks what the re-ordered traversals rely on beyond the topology (point 1): every child box
+ * lies inside its parent's box, so that a leaf box passing the slab test implies all its ancestors pass.  bvh.cc
+ * builds such trees; a caller-supplied tree that does not is rendered with the literal walk (res->loose). */
+__global__ void k_tree_check(const uint32_t *__restrict__ nodes, const float4 *__restrict__ aabbs, uint32_t n, uint32_t leaf_size,
+                             int *__restrict__ delta, TreeResult *res)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const uint32_t size = nodes[i];
 	if (size == 1) return;
 	bool ok = (size & 1u) != 0 && size >= 3 && (uint64_t)i + size <= n;
+	uint32_t l = 0;
 	if (ok) {
-		const uint32_t l = nodes[i + 1];
+		l = nodes[i + 1];
 		ok = (l & 1u) != 0 && l + 2 <= size && nodes[i + 1 + l] == size - 1 - l;
 	}
 	if (!ok) { atomicMin(&res->bad_node, i); return; }
+	{
+		const float4 plo = aabbs[2 * (size_t)i], phi = aabbs[2 * (size_t)i + 1];
+		bool nested = true;
+		for (int k = 0; k < 2; ++k) {
+			const size_t c = k == 0 ? (size_t)i + 1 : (size_t)i + 1 + l;
+			const float4 lo = aabbs[2 * c], hi = aabbs[2 * c + 1];
+			nested = nested && lo.x >= plo.x && lo.y >= plo.y && lo.z >= plo.z && hi.x <= phi.x && hi.y <= phi.y && hi.z <= phi.z;   /* false for NaN */
+		}
+		if (!nested) res->loose = 1u;
+	}
 	if (tree_is_pair(size, i, leaf_size)) {
 		atomicAdd(delta + i + 1, 1);
 		if (i + size < n) atomicAdd(delta + i + size, -1);

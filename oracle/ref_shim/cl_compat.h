@@ -60,8 +60,8 @@ static inline int max(int a, int b) { return a < b ? b : a; }
 static inline float sin(float x) { return (float)std::sin((double)x); }
 static inline float cos(float x) { return (float)std::cos((double)x); }
 static inline float acos(float x) { return (float)std::acos((double)x); }
-static inline float cospi(float x) { return (float)std::cos((double)(3.14159265358979323846f * x)); }
-static inline float sinpi(float x) { return (float)std::sin((double)(3.14159265358979323846f * x)); }
+static inline float cospi(float x) { return (float)std::cos(3.14159265358979323846 * (double)x); }
+static inline float sinpi(float x) { return (float)std::sin(3.14159265358979323846 * (double)x); }
 using std::fabs;
 using std::sqrt;
 

@@ -217,8 +217,8 @@ static inline f4 get_smooth_normal(const orc_scene *sc, const isect_t *isect)
 static inline float t_sin(float x) { return (float)sin((double)x); }
 static inline float t_cos(float x) { return (float)cos((double)x); }
 static inline float t_acos(float x) { return (float)acos((double)x); }
-static inline float t_cospi(float x) { return (float)cos((double)(3.14159265358979323846f * x)); }
-static inline float t_sinpi(float x) { return (float)sin((double)(3.14159265358979323846f * x)); }
+static inline float t_cospi(float x) { return (float)cos(3.14159265358979323846 * (double)x); }
+static inline float t_sinpi(float x) { return (float)sin(3.14159265358979323846 * (double)x); }
 
 static inline f4 f4_muls(f4 a, float s) { return f4_make(a.x * s, a.y * s, a.z * s, a.w * s); }
 

@@ -1,0 +1,134 @@
+"""BASELINE.json configs C3, C4 and C5 at their FULL sizes on the B200, through the C ABI.
+
+The oracle cannot render 132.7 M rays (C3), a 10.16 M-triangle scene at 4K (C4) or 2^28 rays (C5) in seconds, so
+each config is held with the two devices the task allows at full size:
+
+  * sampled rows / a prefix of the batch against the CPU oracle (hit ids, distances, float pixels -- bit-identical;
+    north_star's contractual tolerances are the ones written in tests/test_parity_gpu.py), and
+  * the WHOLE frame / batch against the reference's own algorithm compiled for the GPU (k_render_exhaustive: the
+    stackless pre-order walk of intersect_kernel.cl:184-213 with the literal slab test, no culling, no re-ordering),
+    a size-independent property: two independent traversals must agree on every ray.
+
+Reference anchors: ray generation intersect_kernel.cl:278-310, scene_intersect :184-213, the tree bvh.cc:98-162.
+"""
+import numpy as np
+import pytest
+
+from conftest import require_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _render_with_hits(host, rt, sc, kernel, jitter_seed=0, upload=None):
+    with host.CudaHost(rt, jitter_seed=jitter_seed) as h:
+        h.set_tunable(host.TUNE_KERNEL, kernel)
+        h.set_tunable(host.TUNE_RECORD_HITS, 1)
+        (upload or (lambda hh: hh.upload_scene(sc)))(h)
+        h()
+        st = h.stats()
+        assert st["kernel_variant"] == kernel
+        img = h.download()
+        fid, dist = h.download_hits()
+        return img, fid, dist, st
+
+
+def _same(a, b):
+    """bitwise equality that does not allocate a frame-sized temporary per comparison operand"""
+    return np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("jitter_seed", [0, 0x5EED], ids=["regular_grid", "jittered_16spp"])
+def test_c3_full_frame(po, sibenik_scene, jitter_seed):
+    """C3: sibenik stand-in, 3840x2160 with 16 samples per pixel = 15360 x 8640 = 132 710 400 primary rays; the
+    regular 4x4 grid of the reference and the jittered variant (hash offsets instead of the +0.5f of :287-288)."""
+    host = require_gpu()
+    rt = host.RayTracer(host.Options(width=3840, height=2160, nSuperSamples=16))
+    tw, th = rt.totalWidth, rt.totalHeight
+    assert (tw, th) == (15360, 8640)
+    img, fid, dist, st = _render_with_hits(host, rt, sibenik_scene, host.KERNEL_PERSISTENT, jitter_seed)
+    assert st["rays"] == tw * th
+    # 72 super-sampled rows spread over the frame against the CPU oracle
+    rows = (60, th, 120)
+    ys = list(range(*rows))
+    ref = po.render(sibenik_scene, tw, th, 1.0, True, jitter_seed=jitter_seed, rows=rows)
+    assert len(ys) >= 64
+    bad_id = int((fid[ys] != ref.face_id[ys]).sum())
+    assert bad_id == 0, "%d of %d sampled hit ids differ from the oracle" % (bad_id, len(ys) * tw)
+    assert _same(dist[ys], ref.distance[ys])
+    assert _same(img[ys], ref.image[ys])
+    hit_frac = float((fid[ys] != host.NO_HIT).mean())
+    assert hit_frac > 0.95          # an interior: (almost) every ray hits
+    del ref
+    # the whole frame against the reference's algorithm on the GPU
+    img_x, fid_x, dist_x, _ = _render_with_hits(host, rt, sibenik_scene, host.KERNEL_EXHAUSTIVE, jitter_seed)
+    assert np.array_equal(fid, fid_x), "%d hit ids differ from the literal walk" % int((fid != fid_x).sum())
+    assert _same(dist, dist_x)
+    assert _same(img, img_x)
+
+
+def test_c4_ten_million_triangles(po, scene_mod):
+    """C4: the bunny subdivided 1:144 (10 162 080 triangles, 20.3 M nodes: the node array exceeds the 126 MB L2),
+    3840x2160, one sample per pixel.  The tree is built ON THE DEVICE from the raw mesh (rtx_upload_mesh) and must be
+    the tree bvh.cc:98-162 builds (the host builder that tests/test_scene_prep.py pins to bvh.cc)."""
+    import os
+    host = require_gpu()
+    from opencl_raytracer_b200 import scenes
+    path = po.staged_bunny_path()
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/bunny_mesh.bin not staged (reference tree absent at build time)")
+    v, f = po.read_mesh_bin(path)
+    v, f = scenes.subdivided(v, f)
+    sc = scene_mod.scene_from_mesh(v, f, name="bunny_x144")
+    assert sc.num_triangles == 10162080 and sc.num_nodes == 2 * 10162080 - 1
+    rt = host.RayTracer(host.Options(width=3840, height=2160, nSuperSamples=1))
+    tw, th = rt.totalWidth, rt.totalHeight
+
+    def upload_raw(h):
+        h.upload_mesh(sc.vertices, sc.orig_faces, None)         # tree AND vertex normals on the device
+        nodes, aabbs, tri, faces = h.download_tree()
+        assert np.array_equal(nodes, sc.nodes) and np.array_equal(tri, sc.triangles) and np.array_equal(faces, sc.faces)
+        assert _same(aabbs.reshape(-1), np.ascontiguousarray(sc.aabbs, np.float32).reshape(-1))
+        assert _same(h.download_normals().reshape(-1), np.ascontiguousarray(sc.normals, np.float32).reshape(-1))
+
+    img, fid, dist, st = _render_with_hits(host, rt, sc, host.KERNEL_PERSISTENT, upload=upload_raw)
+    assert st["rays"] == tw * th
+    rows = (15, th, 30)                                          # 72 rows
+    ys = list(range(*rows))
+    ref = po.render(sc, tw, th, 1.0, True, rows=rows)
+    bad_id = int((fid[ys] != ref.face_id[ys]).sum())
+    assert bad_id == 0, "%d of %d sampled hit ids differ from the oracle" % (bad_id, len(ys) * tw)
+    assert _same(dist[ys], ref.distance[ys])
+    assert _same(img[ys], ref.image[ys])
+    assert 0.2 < float((fid != host.NO_HIT).mean()) < 0.6        # bunny + ground plane in a 16:9 frame
+    img_x, fid_x, dist_x, _ = _render_with_hits(host, rt, sc, host.KERNEL_EXHAUSTIVE)
+    assert np.array_equal(fid, fid_x), "%d hit ids differ from the literal walk" % int((fid != fid_x).sum())
+    assert _same(dist, dist_x)
+    assert _same(img, img_x)
+
+
+def test_c5_random_ray_batch(po, sibenik_scene):
+    """C5: 2^28 random-origin, random-direction rays (counter-hash generator, seed 1234) against the stand-in tree:
+    a 2^20 prefix against the oracle, and the (hit count, face-id sum) checksums of the whole batch from the two
+    arbitrary-ray kernels (persistent refill kernel; plain while-while kernel)."""
+    host = require_gpu()
+    rt = host.RayTracer(host.Options(width=32, height=32, nSuperSamples=1))
+    lo, hi = sibenik_scene.root_box()
+    n_chk, total = 1 << 20, 1 << 28
+    o, d = po.gen_random_rays(1234, 0, n_chk, lo, hi)
+    ref = po.trace_rays(sibenik_scene, o, d, 100000.0)
+    sums = {}
+    for incoherent in (1, 0):
+        with host.CudaHost(rt) as h:
+            h.set_tunable(host.TUNE_INCOHERENT_KERNEL, incoherent)
+            h.upload_scene(sibenik_scene)
+            hits, idsum, fid, dist = h.trace_random_rays(1234, 0, n_chk, want_arrays=True)
+            assert np.array_equal(fid, ref.face_id), "%d prefix hit ids differ from the oracle" % int((fid != ref.face_id).sum())
+            assert _same(dist, ref.distance)
+            hit = ref.face_id != host.NO_HIT
+            assert hits == int(hit.sum()) and idsum == int(ref.face_id[hit].astype(np.uint64).sum())
+            sums[incoherent] = h.trace_random_rays(1234, 0, total)[:2]
+            if incoherent:      # the multi-GPU partition (contiguous index ranges over 8 ranks) adds up to the whole batch
+                parts = [h.trace_random_rays(1234, k * (total // 8), total // 8)[:2] for k in range(8)]
+                assert (sum(p[0] for p in parts), sum(p[1] for p in parts)) == sums[1]
+    assert sums[1] == sums[0], "the two arbitrary-ray kernels disagree on the 2^28-ray checksums: %s vs %s" % (sums[1], sums[0])
+    assert 0.85 < sums[1][0] / total < 0.99                      # rays start inside a closed room: most of them hit
