@@ -66,6 +66,24 @@ def make_config(desc, scene_name, ntris, tw, th, world, gather):
                                     "(%d rows = %.2f M rays per pass) on all host cores" % (CPU_ROW_STEP, tw, th, nrows, nrows * tw / 1e6)}
 
 
+def load_profile(workload):
+    """profiles/traffic.json entry of a workload -- only if it was captured on the kernel sources of THIS build
+    (tools/make_traffic.py stamps the sha256 of csrc/ + include/rtx_b200.h).  (entry or None, why)"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        from make_traffic import kernel_source_sha
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            entry = json.load(fh).get(workload)
+    except (OSError, ImportError, ValueError) as e:
+        return None, "profiles/traffic.json unreadable: %s" % e
+    if not entry:
+        return None, "no ncu capture of workload %s in profiles/traffic.json" % workload
+    have, want = (entry.get("stamp") or {}).get("kernel_src_sha16"), kernel_source_sha()
+    if have != want:
+        return None, "stale: profiles/traffic.json[%s] was captured on kernel sources %s, this build is %s" % (workload, have, want)
+    return entry, "ncu --set full, %s, kernel sources %s" % (entry["stamp"].get("report"), want)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -202,6 +220,104 @@ def oracle_counters(sc, tw, th):
     r = po.render(sc, tw, th, 1.0, True, rows=(step // 2, th, step), want_ids=False, want_counters=True)
     c = r.counters
     return c["V"], c["T"], c["h"]
+
+
+def extra_c4(local_rank, peak):
+    """BASELINE config 4 inside the default line (N = 1): bunny x144 = 10 162 080 triangles (node array > L2) at
+    3840x2160, one sample per pixel.  Tree built on the device from the raw mesh; value = best kernel time of 5 frames;
+    parity = sampled rows against the oracle + the whole frame against the literal walk on the GPU."""
+    from opencl_raytracer_b200 import host
+    from oracle import pyoracle as po
+    if not os.path.exists(po.staged_bunny_path()):
+        return {"unavailable": "oracle/_ref/bunny_mesh.bin not staged"}
+    sc = build_scene("bunny_x144")
+    rt = host.RayTracer(host.Options(width=3840, height=2160, nSuperSamples=1))
+    tw, th = rt.totalWidth, rt.totalHeight
+    out = {}
+    with host.CudaHost(rt, device=local_rank) as h:
+        t0 = time.perf_counter()
+        h.upload_mesh(sc.vertices, sc.orig_faces, None)
+        wall = (time.perf_counter() - t0) * 1e3
+        bms, levels = h.build_stats()
+        best = 1e9
+        for _ in range(5):
+            h()
+            best = min(best, h.stats()["kernel_ms"])
+        h.set_tunable(host.TUNE_RECORD_HITS, 1)          # parity frame: ids + distances recorded (not timed)
+        h()
+        img = h.download()
+        fid, dist = h.download_hits()
+    rows = (45, th, 90)
+    ys = list(range(*rows))
+    ref = po.render(sc, tw, th, 1.0, True, rows=rows, want_counters=True)
+    V, T, hf = ref.counters["V"], ref.counters["T"], ref.counters["h"]
+    with host.CudaHost(rt, device=local_rank) as h:
+        h.set_tunable(host.TUNE_KERNEL, host.KERNEL_EXHAUSTIVE)
+        h.set_tunable(host.TUNE_RECORD_HITS, 1)
+        h.upload_scene(sc)
+        h()
+        lit_ms = h.stats()["kernel_ms"]
+        fid_x, dist_x = h.download_hits()
+        img_x = h.download()
+    prof, prof_src = load_profile("c4")
+    hbm = None
+    if prof:
+        tr = (prof.get("dram_bytes_read") or 0) + (prof.get("dram_bytes_write") or 0)
+        hbm = {"dram_bytes_per_frame": tr, "GBps": tr / (best * 1e-3) / 1e9, "frac_of_peak": tr / (best * 1e-3) / 1e9 / peak,
+               "warps_active_pct": prof.get("warps_active_pct"), "avg_threads_per_instruction": prof.get("avg_threads_per_instruction"),
+               "l2_hit_pct": prof.get("l2_hit_pct"), "kernel": prof.get("kernel")}
+    B = 32.0 * V + 48.0 * T + 48.0 * hf + 4.0
+    out.update({
+        "workload": WORKLOADS["c4"][4], "triangles": sc.num_triangles, "rays": tw * th, "kernel_ms": best, "Mrays/s": tw * th / best / 1e3,
+        "device_build_ms": bms, "build_levels": levels, "rtx_upload_mesh_wall_ms": wall,
+        "parity": {"rows_vs_oracle": len(ys), "rays_vs_oracle": len(ys) * tw,
+                   "id_mismatches": int((fid[ys] != ref.face_id[ys]).sum()),
+                   "distance_mismatches": int((dist[ys].view(np.uint32) != ref.distance[ys].view(np.uint32)).sum()),
+                   "pixel_mismatches": int((img[ys].view(np.uint32) != ref.image[ys].view(np.uint32)).sum()),
+                   "whole_frame_vs_literal_walk_on_gpu": {"id_mismatches": int((fid != fid_x).sum()),
+                                                          "distance_mismatches": int((dist.view(np.uint32) != dist_x.view(np.uint32)).sum()),
+                                                          "pixel_mismatches": int((img.view(np.uint32) != img_x.view(np.uint32)).sum()),
+                                                          "literal_walk_ms": lit_ms}},
+        "algorithmic_vs_hbm": {"bytes_per_ray": B, "V": V, "T": T, "h": hf, "GBps": B * tw * th / (best * 1e-3) / 1e9,
+                               "frac": B * tw * th / (best * 1e-3) / 1e9 / peak},
+        "hbm_measured": hbm, "profile": prof_src})
+    return out
+
+
+def extra_c5(local_rank, sc, peak):
+    """BASELINE config 5 inside the default line (N = 1): 2^28 random rays (counter-hash generator, seed 1234) against the
+    stand-in tree; value = best device time of 3 batches; parity = a 2^16 prefix against the oracle + checksums."""
+    from opencl_raytracer_b200 import host
+    from oracle import pyoracle as po
+    rt = host.RayTracer(host.Options(width=32, height=32, nSuperSamples=1))
+    total, n_chk = 1 << 28, 1 << 16
+    lo, hi = sc.root_box()
+    o, d = po.gen_random_rays(1234, 0, n_chk, lo, hi)
+    ref = po.trace_rays(sc, o, d, 100000.0, want_counters=True)
+    with host.CudaHost(rt, device=local_rank) as h:
+        h.upload_scene(sc)
+        _, _, fid, dist = h.trace_random_rays(1234, 0, n_chk, want_arrays=True)
+        best, sums = 1e9, None
+        h.trace_random_rays(1234, 0, 1 << 24)
+        for _ in range(3):
+            hits, idsum, _, _ = h.trace_random_rays(1234, 0, total)
+            best = min(best, h.stats()["kernel_ms"])
+            sums = (hits, idsum)
+    V, T, hf = ref.counters["V"], ref.counters["T"], ref.counters["h"]
+    B = 32.0 * V + 48.0 * T + 48.0 * hf + 4.0 + 8.0
+    prof, prof_src = load_profile("c5")
+    issue = None
+    if prof:
+        issue = {"ncu_issue_active_pct": prof.get("issue_active_pct"), "avg_threads_per_instruction": prof.get("avg_threads_per_instruction"),
+                 "l1tex_throughput_pct": prof.get("l1tex_throughput_pct"), "warps_active_pct": prof.get("warps_active_pct"), "kernel": prof.get("kernel")}
+    return {"workload": WORKLOADS["c5"][4], "rays": total, "kernel_ms": best, "Mrays/s": total / best / 1e3,
+            "parity": {"rays_vs_oracle": n_chk, "id_mismatches": int((fid != ref.face_id).sum()),
+                       "distance_mismatches": int((dist.view(np.uint32) != ref.distance.view(np.uint32)).sum()),
+                       "hit_count": sums[0], "face_id_sum": sums[1]},
+            "algorithmic_vs_hbm": {"bytes_per_ray": B, "V": V, "T": T, "h": hf, "GBps": B * total / (best * 1e-3) / 1e9,
+                                   "frac": B * total / (best * 1e-3) / 1e9 / peak,
+                                   "note": "tree is L2-resident; see profiles/ for the DRAM traffic (tens of MB per launch)"},
+            "profiled": issue, "profile": prof_src, "sweep_over_gpus": "python bench.py --workload c5 --gpus N (profiles/r2_c5_scaling.json)"}
 
 
 def bench_c5(args, rank, world, local_rank, desc):
@@ -612,6 +728,9 @@ def main():
             extras["ambient_occlusion_c2_frame"] = {"kernel_ms": ms, "primary_Mrays/s": rt_ao.totalWidth * rt_ao.totalHeight / ms / 1e3,
                                                     "what": "3840x2160 primary rays + uniform AO with 3 rings (28 occlusion rays per hit pixel, "
                                                             "intersect_kernel.cl:214-277); %.1f %% of the pixels are lit" % (100 * hit)}
+        peak_hbm = load_peaks()[0]
+        extras["c5"] = extra_c5(local_rank, sc, peak_hbm) if args.workload == "c3" else None
+        extras["c4"] = extra_c4(local_rank, peak_hbm) if args.workload == "c3" else None
         extras["reference_algorithm_on_gpu"]["what"] = ("k_render_exhaustive: the reference kernel's own algorithm (one thread per pixel, "
                                                         "stackless pre-order walk, no culling) compiled for sm_100a")
 
@@ -621,58 +740,58 @@ def main():
         V, T, hfrac = oracle_counters(sc, tw, th)
         B = 32.0 * V + 48.0 * T + 48.0 * hfrac + 4.0
         peak, peak_src = load_peaks()
-        k_rays = rays / world if world > 1 else rays
-        achieved = B * k_rays / (kernel_ms_mean * 1e-3) / 1e9
-        l2_peak = r.host.probe_bandwidth(0, 32 << 20, 20)
-        prof = {}
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                prof = json.load(fh).get(args.workload, {})
-        except OSError:
-            pass
-        traffic = (prof.get("dram_bytes_read", 0) + prof.get("dram_bytes_write", 0)) or None
-        if traffic and world > 1:
-            traffic = traffic / world
         kernel_s = kernel_ms_mean * 1e-3
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "peak_source": peak_src,
-                    "kernel": "k_render_packet<MODE 1> (candidate-list kernel; ~96 % of the traversal time, with k_frustum_collect* "
-                              "and the overflow launch inside the same event pair; profiles/r1_c3_final_launches.csv)",
-                    "kernel_ms": kernel_ms_mean,
-                    "algorithmic_bytes_per_ray": B, "V": V, "T": T, "h": hfrac,
-                    "note": "SURVEY 8d algorithmic bytes follow the reference's exhaustive walk (V box tests, T triangle tests per ray). "
-                            "The scene (11 MB) is L2/L1-resident and the frustum front end tests ~7 leaf boxes + ~4 triangles per ray "
-                            "instead, so this fraction exceeds 1; the traffic that really reaches HBM is `traffic` (essentially the "
-                            "4 B/ray image write) and the kernel is instruction-issue bound (see `issue`).",
-                    "hbm_actual": ({"bytes_per_launch": traffic, "GBps": traffic / kernel_s / 1e9, "frac_of_peak": traffic / kernel_s / 1e9 / peak}
-                                   if traffic else None),
-                    "l2": {"achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
-                           "peak_source": "rtx_probe_bandwidth: ld.cg float4 sweep of a 32 MiB buffer, this run"},
-                    "issue": ({"issue_active_pct": prof.get("issue_active_pct"), "warp_instructions": prof.get("warp_instructions"),
-                               "avg_threads_per_instruction": prof.get("avg_threads_per_instruction"),
-                               "source": "ncu --set full, profiles/r1_c3_final_ncu.txt"} if prof else None)}
-        if prof.get("l1_load_bytes") and kernel_s > 0 and world == 1:
-            # bytes per launch from the ncu capture (fixed for the workload) over the kernel time measured in this run
-            frac_list = prof.get("share_of_kernel_ms_pct", 100.0) / 100.0
-            roofline["measured_traffic"] = {
-                "l1_load_GBps": prof["l1_load_bytes"] / (kernel_s * frac_list) / 1e9, "l1_hit_pct": prof.get("l1_hit_pct"),
-                "l2_read_GBps": prof["l2_read_bytes_from_l1"] / (kernel_s * frac_list) / 1e9, "l2_hit_pct": prof.get("l2_hit_pct"),
-                "l2_frac_of_probed_peak": prof["l2_read_bytes_from_l1"] / (kernel_s * frac_list) / 1e9 / l2_peak,
-                "hbm_GBps": traffic / (kernel_s * frac_list) / 1e9 if traffic else None,
-                "source": "l1tex__t_sectors_pipe_lsu_mem_global_op_ld, lts__t_sectors_srcunit_tex_op_read, dram__bytes_* (%s)" % prof.get("source", "profiles/")}
-        if prof.get("warp_instructions") and prof.get("duration_ms") and clocks.get("sm_mhz"):
-            # the bound that actually holds: warp instructions issued per second against 4 schedulers x 1 instruction
-            # per clock per SM.  Instruction count from the ncu capture of this kernel (fixed for the workload),
-            # time and clock measured in this run.
-            sms = host.device_info(local_rank).sm_count
-            list_ms = kernel_ms_mean * (prof.get("share_of_kernel_ms_pct", 100.0) / 100.0) if world == 1 else None
-            if list_ms:
-                ach = prof["warp_instructions"] / (list_ms * 1e-3) / 1e9
+        k_rays = rays / world
+        alg_gbps = B * k_rays / kernel_s / 1e9
+        l2_peak = r.host.probe_bandwidth(0, 32 << 20, 20)
+        # profiler-only quantities (instruction count, bytes per memory level) come from a capture of THIS build at
+        # N = 1, or not at all: a stale or other-N capture is never scaled into the line
+        prof, prof_src = load_profile(args.workload) if world == 1 else (None, "captures are per N; only the 1-GPU launch is profiled")
+        sms = host.device_info(local_rank).sm_count
+        share = (prof or {}).get("share_of_kernel_ms_pct", 100.0) / 100.0      # dominant kernel's share of the event pair
+        issue = hbm_actual = levels = None
+        traffic = None
+        if prof:
+            dom_s = kernel_s * share
+            traffic = (prof.get("dram_bytes_read") or 0) + (prof.get("dram_bytes_write") or 0)
+            hbm_actual = {"bytes_per_launch": traffic, "GBps": traffic / dom_s / 1e9, "frac_of_peak": traffic / dom_s / 1e9 / peak,
+                          "compulsory_bytes": 4 * rays, "note": "compulsory HBM traffic of this workload is the 4 B/ray image write"}
+            if prof.get("warp_instructions") and clocks.get("sm_mhz"):
+                ach = prof["warp_instructions"] / dom_s / 1e9
                 pk = sms * 4 * clocks["sm_mhz"] * 1e6 / 1e9
-                roofline["issue_roofline"] = {"bound": "warp-instruction issue", "achieved": ach, "peak": pk, "unit": "Gwarp-instr/s", "frac": ach / pk,
-                                              "how": "warp instructions of the list kernel (ncu, %s) / (kernel_ms x its %.1f %% share of the event pair); "
-                                                     "peak = %d SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the timed region)"
-                                                     % (prof.get("source", "profiles/"), prof.get("share_of_kernel_ms_pct", 100.0), sms, clocks["sm_mhz"])}
+                issue = {"achieved": ach, "peak": pk, "frac": ach / pk,
+                         "warp_instructions_per_launch": prof["warp_instructions"],
+                         "thread_instructions_per_ray": (prof["warp_instructions"] * (prof.get("avg_threads_per_instruction") or 32.0)) / rays,
+                         "avg_threads_per_instruction": prof.get("avg_threads_per_instruction"),
+                         "ncu_issue_active_pct": prof.get("issue_active_pct"), "ncu_warps_active_pct": prof.get("warps_active_pct"),
+                         "how": "warp instructions of the dominant kernel (ncu capture of this build) / (kernel_ms of this run x its %.1f %% share "
+                                "of the event pair); peak = %d SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the timed region)"
+                                % (100 * share, sms, clocks["sm_mhz"])}
+            if prof.get("l1_load_bytes") and prof.get("l2_read_bytes_from_l1"):
+                levels = {"l1_load_GBps": prof["l1_load_bytes"] / dom_s / 1e9, "l1_hit_pct": prof.get("l1_hit_pct"),
+                          "l2_read_GBps": prof["l2_read_bytes_from_l1"] / dom_s / 1e9, "l2_hit_pct": prof.get("l2_hit_pct"),
+                          "l2_peak_GBps_probed": l2_peak, "l2_frac_of_probed_peak": prof["l2_read_bytes_from_l1"] / dom_s / 1e9 / l2_peak,
+                          "hbm_GBps": traffic / dom_s / 1e9, "hbm_frac_of_peak": traffic / dom_s / 1e9 / peak}
+        # top level = the level that binds.  The scene (11 MB) lives in L1/L2, the only compulsory HBM traffic is the
+        # image write (2 % of peak), so the bound is warp-instruction issue; SURVEY 8d's algorithmic-bytes figure is kept
+        # beside it (algorithmic_vs_hbm) with the reason it exceeds 1.
+        roofline = {
+            "bound": "issue", "unit": "Gwarp-instr/s",
+            "achieved": issue["achieved"] if issue else None, "peak": issue["peak"] if issue else None,
+            "frac": issue["frac"] if issue else None,
+            "traffic": traffic,
+            "kernel": (prof or {}).get("kernel", "k_render_packet<256,4,0,...,2,1,1> (candidate-list kernel)"),
+            "kernel_ms": kernel_ms_mean, "dominant_kernel_share_of_kernel_ms": share if prof else None,
+            "profile": prof_src, "peak_source": "148 SMs x 4 warp schedulers x 1 instruction / clock at the sampled SM clock",
+            "issue": issue, "hbm_actual": hbm_actual, "memory_levels": levels,
+            "algorithmic_vs_hbm": {
+                "bound": "hbm", "achieved": alg_gbps, "peak": peak, "unit": "GB/s", "frac": alg_gbps / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_ray": B, "V": V, "T": T, "h": hfrac,
+                "note": "SURVEY 8d contract figure: B = 32 V + 48 T + 48 h + 4 bytes per ray under the reference's EXHAUSTIVE walk "
+                        "(V box tests, T triangle tests per ray, counted by the oracle on a row sample of this frame) x rays / kernel time. "
+                        "It exceeds 1 because the kernel does not do that work: the frustum front end leaves ~7 leaf-box and ~4 triangle "
+                        "tests per ray and the scene is cache-resident; results are bit-identical (parity_check). Not a roofline fraction."},
+            "l2_probe": {"peak_GBps": l2_peak, "source": "rtx_probe_bandwidth: ld.cg float4 sweep of a 32 MiB buffer, this run"}}
         if world == 1 and not args.no_cpu:
             arm = CpuArm(sc, tw, th)
             passes, total_s = arm.run_for(10.0)

@@ -301,6 +301,7 @@ struct Work {
 	float *dist;
 	float2 *hit_st;              /* optional (ambient occlusion): parametric coordinates of the hit */
 	int ordered_ok;
+	int cost_map;                /* analysis hook: record mode stores the SM cycles a ray's warp took instead of the distance */
 	int frustum;                 /* use the frustum front end for packets */
 	const uint32_t *lists;       /* per-tile candidate lists written by k_frustum_collect */
 	unsigned int *overflow_tiles; /* number of tiles whose list overflowed (zeroed before launch) */
@@ -325,13 +326,14 @@ RTX_DEV void trace_pixel(const SceneDev &sc, const Work &w, const float4 *s_top,
 	const f3 o = make_f3(0.0f, 0.0f, 2.0f);                           /* :284 */
 	const f3 d = primary_dir(w.cam, x, y);
 	HitRec best;
+	const long long t0 = (RECORD && w.cost_map) ? clock64() : 0ll;
 	closest_hit<SMEM_STACK, TOP_SMEM, COUNT, true>(sc, s_top, s_stack, w.ordered_ok != 0, o, d, 100000.0f, best, cnt); /* :292-295 */
 	float value = 0.0f;                                               /* :297-299 */
 	if (best.tri != 0xffffffffu) value = shade_hit(sc.tnormals, best.tri, best.s, best.t, d, w.cam.shading);
 	w.image[out] = value;                                             /* :309 */
 	if (RECORD) {
 		w.face_id[out] = best.tri != 0xffffffffu ? best.tri * 3u : 0xffffffffu;
-		w.dist[out] = best.dist;
+		w.dist[out] = w.cost_map ? (float)(clock64() - t0) : best.dist;     /* cost_map: analysis hook (tools/cost_map.py) */
 		if (w.hit_st) w.hit_st[out] = make_float2(best.s, best.t);
 	}
 }
