@@ -60,7 +60,9 @@ def make_config(desc, scene_name, ntris, tw, th, world, gather):
     return {"workload": desc, "scene": scene_name, "triangles": int(ntris), "rays_per_step": int(tw * th),
             "parallelism": "interleaved 32x32 tiles over %d GPU(s), scene replicated, 1 NCCL gather/frame" % world,
             "step": "trace + RayTracer::resize on the device%s -> %s image on rank 0" % (
-                " + 1 NCCL gather + de-interleave" if world > 1 else "", "byte" if gather == "u8" else "float"),
+                "" if world == 1 else (" + 1 NCCL gather + de-interleave" if not gather.startswith("p2p_") else
+                                       ", every rank's kernel storing its share into rank 0's image over NVLink peer memory + 1-element all-reduce"),
+                "byte" if gather.endswith("u8") else "float"),
             "l2": "flushed between timed iterations (256 MiB memset, untimed)",
             "reference_arm_sample": "the CPU arm (--impl reference, cpu_baseline) times every %d-th row of the same %dx%d frame "
                                     "(%d rows = %.2f M rays per pass) on all host cores" % (CPU_ROW_STEP, tw, th, nrows, nrows * tw / 1e6)}
@@ -453,9 +455,11 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="u8", choices=["u8", "float"],
-                    help="what a step ends with on rank 0: the byte image after RayTracer::resize on the device (default; "
-                         "every rank resizes its own tiles, the NCCL gather moves bytes) or the float image (gather moves floats)")
+    ap.add_argument("--gather", default="u8", choices=["u8", "float", "p2p_u8", "p2p_float"],
+                    help="what a step ends with on rank 0 and how it gets there (N > 1): u8 = the byte image after RayTracer::resize on "
+                         "the device, every rank resizes its own tiles and ONE NCCL gather moves bytes (default); float = ONE NCCL gather "
+                         "of the float tiles; p2p_* = no collective, every rank's kernel stores its share into rank 0's image over NVLink "
+                         "peer memory (multigpu.TiledRenderer)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -564,6 +568,33 @@ def main():
     value = rays * args.steps / (total_ms * 1e-3) / 1e6
     kernel_ms_mean = float(km.item())
 
+    # per-phase device times (CUDA events around every launch group; separate frames, not the timed ones)
+    phase_names = list(host.PHASES) + ["resize", "gather", "deinterleave"]
+    r.host.set_tunable(host.TUNE_PHASE_TIMING, 1)
+    r.timing = True
+    acc = np.zeros(len(phase_names))
+    nph = 5
+    for _ in range(nph):
+        flush.zero_()
+        if world > 1:
+            dist.all_reduce(rendezvous)
+        r.render_frame()
+        torch.cuda.synchronize(dev)
+        ph = r.phase_ms()
+        acc += np.array([ph.get(k, 0.0) for k in phase_names])
+    r.host.set_tunable(host.TUNE_PHASE_TIMING, 0)
+    r.timing = False
+    pt = torch.tensor(acc / nph, dtype=torch.float64, device=dev)
+    pt_mean = pt.clone()
+    if world > 1:
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pt_mean)
+        pt_mean /= world
+    phases_ms = {"max_over_ranks": {k: float(v) for k, v in zip(phase_names, pt.cpu().numpy())},
+                 "mean_over_ranks": {k: float(v) for k, v in zip(phase_names, pt_mean.cpu().numpy())},
+                 "how": "CUDA events around each launch group of %d extra frames (rtx_phase_ms + torch events in multigpu.TiledRenderer); "
+                        "'gather' = the NCCL gather (or, p2p modes, the all-reduce that orders the ranks), 'resize' includes the peer stores in p2p_u8" % nph}
+
     # parity spot check inside the bench (rank 0): sampled rows of the gathered frame == oracle
     parity = None
     if rank == 0:
@@ -574,7 +605,7 @@ def main():
         ref = np.zeros((th, tw), np.float32)
         for k in range(n):                                       # their n super-sampled rows each
             ref += po.render(sc, tw, th, 1.0, True, rows=(ys[0] * n + k, th, ystep * n), want_ids=False).image
-        if args.gather == "u8":
+        if args.gather.endswith("u8"):
             got = r.download_u8()
             want = po.resize(ref, width, height, n)
             parity = {"rows_checked": len(ys), "image": "u8 %dx%d" % (width, height),
@@ -586,24 +617,37 @@ def main():
                       "pixels_differing": int((got[sel] != ref[sel]).sum())}
         del got, ref
 
-    # N > 1: the same frame with the other gather payload, for comparison
+    # N > 1: the same frame with the other ways of getting it to rank 0, for comparison
     other = None
     if world > 1:
-        alt = "float" if args.gather == "u8" else "u8"
-        r2 = multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather=alt)
-        for _ in range(2):
-            r2.render_frame()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(4):
-            r2.render_frame()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        tms = torch.tensor([e0.elapsed_time(e1) / 4], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        other = {"gather": alt, "ms_per_step": float(tms.item()), "value": rays / (float(tms.item()) * 1e-3) / 1e6, "unit": "Mrays/s"}
-        r2.close()
+        other = []
+        for alt in ("u8", "float", "p2p_u8", "p2p_float"):
+            if alt == args.gather:
+                continue
+            try:
+                r2 = multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather=alt)
+            except RuntimeError as e:                    # peer memory not available between these GPUs (all ranks agree)
+                other.append({"gather": alt, "unavailable": str(e)})
+                continue
+            for _ in range(3):
+                r2.render_frame()
+            barrier()
+            ts = []
+            for _ in range(6):
+                flush.zero_()
+                dist.all_reduce(rendezvous)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r2.render_frame()
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ts.append(e0.elapsed_time(e1))
+            tms = torch.tensor(ts, dtype=torch.float64, device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.mean().item())
+            other.append({"gather": alt, "ms_per_step": ms, "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s"})
+            barrier()
+            r2.close()
 
     # ---------------- e2e: the reference's five calls on host buffers ----------------
     e2e = e2e_u8 = None
@@ -648,8 +692,40 @@ def main():
             if rank == 0:
                 timed("download", lambda: r_u8.host.download_u8(out_b))
 
+        shared = None
+        if world > 1:
+            try:
+                shared = multigpu.SharedHostImage(rt, rank, world)
+            except RuntimeError as e:                    # e.g. a small /dev/shm: keep the gather path as the headline
+                shared_note = str(e)
+
+        def frame_shared():
+            # N > 1: the caller's float image is one page-locked host buffer every rank maps; each rank uploads, traces its tiles
+            # and stores them straight into it over its OWN PCIe link (rtx_store_tiles_async) -- no gather, no rank-0 funnel
+            st = torch.cuda.current_stream(dev).cuda_stream
+            timed("upload", lambda: r_float.host.upload(*np_arrs))
+
+            def go():
+                r_float.host.render_async(st)
+                r_float.host.store_tiles_async(shared.device_ptr, st)
+                torch.cuda.synchronize(dev)
+            timed("render+store", go)
+
+        def frame_shared_direct():
+            # the same, without the store kernel: the traversal kernel itself writes each pixel into the mapped host image
+            # (rtx_bind_output_image), so the PCIe transfer overlaps the tracing
+            st = torch.cuda.current_stream(dev).cuda_stream
+            timed("upload", lambda: r_float.host.upload(*np_arrs))
+
+            def go():
+                r_float.host.bind_output_image(shared.device_ptr)
+                r_float.host.render_async(st)
+                torch.cuda.synchronize(dev)
+                r_float.host.bind_output(r_float.local.data_ptr(), r_float.local.numel())
+            timed("render(into host image)", go)
+
         res, phases = [], []
-        fns = (frame_float, frame_u8) + ((frame_pipelined,) if world == 1 else ())
+        fns = (frame_float, frame_u8) + ((frame_pipelined,) if world == 1 else ()) + ((frame_shared, frame_shared_direct) if shared is not None else ())
         for fn in fns:
             for _ in range(2):
                 fn()
@@ -670,6 +746,24 @@ def main():
         e2e = {"value": res[0], "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": rays * 4,
                "calls": "rtx_upload + rtx_render(+gather) + rtx_download(float image), pinned host buffers, wall clock",
                "phase_ms": phases[0]}
+        if world > 1 and shared is not None:
+            via_gather = e2e
+            same = None
+            if rank == 0:                                # the two host images must be the same image
+                same = bool(np.array_equal(np.asarray(shared.array).view(np.uint32), out_f.view(np.uint32)))
+            best = 3 if res[3] >= res[2] else 2
+            calls = ("per rank: rtx_upload + rtx_bind_output_image(host image) + rtx_render_async: the traversal kernel writes its pixels "
+                     "straight into ONE page-locked host image mapped by every rank process (multigpu.SharedHostImage, rtx_host_register)",
+                     "per rank: rtx_upload + rtx_render_async + rtx_store_tiles_async into ONE page-locked host image mapped by every "
+                     "rank process (multigpu.SharedHostImage, rtx_host_register)")
+            e2e = {"value": res[best], "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": rays * 4,
+                   "calls": calls[0 if best == 3 else 1] + ": each rank's tiles leave over its own PCIe link; wall clock incl. a barrier per frame",
+                   "phase_ms": phases[best], "identical_to_gathered_image": same,
+                   "store_kernel_variant": {"value": res[2], "phase_ms": phases[2]}, "direct_render_variant": {"value": res[3], "phase_ms": phases[3]},
+                   "via_rank0_gather": {"value": via_gather["value"], "calls": via_gather["calls"], "phase_ms": via_gather["phase_ms"]}}
+            shared.close()
+        elif world > 1:
+            e2e["note"] = "shared host image unavailable (%s): rank 0 downloads the gathered frame" % shared_note
         if world == 1:
             # the headline end-to-end figure: same host buffers, same bytes over PCIe, the library's fused call
             e2e_three_calls = e2e
@@ -805,7 +899,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": make_config(desc, sc.name, sc.num_triangles, tw, th, world, args.gather),
             "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(lt.item()),
-            "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "other_gather": other, "extras": extras,
+            "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "phases_ms": phases_ms, "other_gather": other, "extras": extras,
             "step_ms": [float(x) for x in step_ms],
         }))
     if world > 1:

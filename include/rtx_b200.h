@@ -111,6 +111,7 @@ typedef struct rtx_stats {
 #define RTX_TUNE_FRUSTUM       9  /* frustum front end for 16x8-pixel packets: 0 off, 1 on, -1 auto */
 #define RTX_TUNE_LIST_RAYS_PER_THREAD 10 /* rays per lane in the candidate-list kernel: 1, 2 or 4 */
 #define RTX_TUNE_RAY_TABLES    12  /* 1 (default): per-column/row tables of the pixel terms of the primary ray direction */
+#define RTX_TUNE_PHASE_TIMING  13  /* 1: CUDA events around every launch group of a frame, read back with rtx_phase_ms */
 #define RTX_TUNE_INCOHERENT_KERNEL 11 /* arbitrary rays: 1 persistent refill + parked leaves (default), 0 plain while-while */
 
 #define RTX_KERNEL_PERSISTENT  0  /* persistent warps, ordered stack traversal, distance culling */
@@ -196,6 +197,12 @@ int rtx_device_image(rtx_ctx *ctx, void **device_ptr, size_t *count);
  * rtx_device_image reports.  device_ptr == NULL restores the internal buffer. */
 int rtx_bind_output(rtx_ctx *ctx, void *device_ptr, size_t count);
 
+/* tile_world > 1: render this rank's tiles straight into the WHOLE row-major total_width*total_height float image at
+ * `image_f32` -- rank 0's device memory mapped over NVLink (rtx_peer_open) or page-locked host memory mapped into the
+ * device (rtx_host_register).  Each pixel leaves the SM as it is shaded: the transfer overlaps the tracing and needs
+ * no kernel, gather or copy of its own.  Float image only (no hit records, no ambient occlusion).  NULL unbinds. */
+int rtx_bind_output_image(rtx_ctx *ctx, void *image_f32);
+
 /* Closest hit for arbitrary rays (config C5), reference scene_intersect
  * semantics with the given max_distance.  origins/dirs: 4 floats per ray.
  * Host-pointer and device-pointer forms.  The host form cuts a large batch into
@@ -235,6 +242,41 @@ int rtx_deinterleave_u8_async(rtx_ctx *ctx, const void *d_gathered_u8, uint32_t 
 /* Scatter `world` gathered compact buffers (rank-major, tiles_per_rank*1024
  * floats each) into the row-major image of this context (rank 0). */
 int rtx_deinterleave_async(rtx_ctx *ctx, const void *d_gathered, uint32_t world, void *stream);
+
+/* ---- direct stores: no collective, every rank writes its share into the final image itself ----
+ *
+ * The final image may live in this rank's device memory, in rank 0's (mapped with rtx_peer_open: the stores cross
+ * NVLink / NVSwitch, resize + gather + de-interleave become one kernel per rank) or in page-locked host memory mapped
+ * into the device (rtx_host_register: every rank's tiles leave over its OWN PCIe link instead of funnelling through
+ * rank 0's).  The caller orders the ranks (e.g. a one-element all-reduce on the same stream after the store: it
+ * completes on rank 0 only when every rank's store kernel has finished).
+ *   rtx_resize_u8_to_async   RayTracer::resize (ray_tracer.cc:3-15) of this rank's tiles -> row-major width*height bytes
+ *   rtx_store_tiles_async    this rank's float tiles -> row-major total_width*total_height floats
+ *   rtx_adopt_u8             rtx_download_u8 of this context reads the finished bytes from d_image_u8 */
+int rtx_resize_u8_to_async(rtx_ctx *ctx, void *image_u8, void *stream);
+int rtx_store_tiles_async(rtx_ctx *ctx, void *image_f32, void *stream);
+int rtx_adopt_u8(rtx_ctx *ctx, const void *d_image_u8);
+
+/* Device memory that other rank processes can map (CUDA IPC; 64-byte handle, any transport). */
+int rtx_peer_alloc(rtx_ctx *ctx, size_t bytes, void **device_ptr, unsigned char handle[64]);
+int rtx_peer_open(rtx_ctx *ctx, const unsigned char handle[64], void **device_ptr);
+int rtx_peer_close(rtx_ctx *ctx, void *device_ptr);
+int rtx_peer_free(rtx_ctx *ctx, void *device_ptr);
+int rtx_copy_to_host(rtx_ctx *ctx, void *host_dst, const void *device_src, size_t bytes);   /* blocking, after all queued work */
+
+/* Page-lock and device-map caller-owned host memory (a shared mapping several rank processes opened). */
+int rtx_host_register(void *p, size_t bytes, void **device_alias);
+int rtx_host_unregister(void *p);
+
+/* Device time of each launch group of the last frame rendered with RTX_TUNE_PHASE_TIMING set (ms[RTX_NUM_PHASES]). */
+#define RTX_PHASE_TABLES        0   /* per-column / per-row ray tables */
+#define RTX_PHASE_COLLECT_SUPER 1   /* frustum front end, 128x128-pixel super-tiles */
+#define RTX_PHASE_COLLECT       2   /* frustum front end, 32x32-pixel tiles */
+#define RTX_PHASE_TRAVERSAL     3   /* candidate-list kernel, or the per-ray traversal kernel */
+#define RTX_PHASE_OVERFLOW      4   /* per-ray traversal of the tiles whose list overflowed */
+#define RTX_PHASE_AO            5   /* ambient-occlusion pass */
+#define RTX_NUM_PHASES          6
+int rtx_phase_ms(const rtx_ctx *ctx, double *ms);
 
 #ifdef __cplusplus
 }

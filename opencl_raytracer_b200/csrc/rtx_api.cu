@@ -98,12 +98,19 @@ struct rtx_ctx {
 	uint32_t W = 0, H = 0, tiles_x = 0, tiles_y = 0, tiles_per_rank = 0, local_tiles = 0;
 	uint32_t rank = 0, world = 1;
 	float *ext_image = nullptr;  /* caller-owned output (rtx_bind_output) */
+	bool ext_rowmajor = false;   /* ... and it is the whole row-major image although tile_world > 1 (rtx_bind_output_image) */
 	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums, d_lists, d_slists, d_raytab;
 	DevBuf d_hit_st, d_ao_ring;  /* ambient occlusion: (s, t) of the primary hits; sample table of the uniform method */
 	bool ao = false;
 	float ao_max_distance = 0.f; /* after the compiler_options.h round trip */
 	uint32_t ao_ring_cap = 0;
 	bool rendered = false, full_valid = false, u8_valid = false;
+	const unsigned char *ext_u8 = nullptr;   /* rtx_adopt_u8: the finished byte image lives in caller-owned device memory */
+	/* per-phase device times of one frame (RTX_TUNE_PHASE_TIMING): marks around each launch group */
+	int phase_timing = 0;
+	cudaEvent_t ph_ev[RTX_NUM_PHASES + 1] = {};
+	bool ph_rec[RTX_NUM_PHASES + 1] = {};
+	double phase_ms[RTX_NUM_PHASES] = {};
 	/* stats */
 	rtx_stats stats{};
 };
@@ -290,6 +297,16 @@ cudaError_t resident_blocks(K kernel, int block, size_t smem, int device, int *o
 	return cudaSuccess;
 }
 
+/* Phase timing (RTX_TUNE_PHASE_TIMING): mark k is recorded right before phase k is enqueued, mark RTX_NUM_PHASES at the
+ * end of the frame; a phase lasts from its mark to the next recorded one (finish_stats). */
+cudaError_t phase_mark(rtx_ctx *c, cudaStream_t st, int k)
+{
+	if (!c->phase_timing) return cudaSuccess;
+	if (!c->ph_ev[k]) { cudaError_t e = cudaEventCreate(&c->ph_ev[k]); if (e != cudaSuccess) return e; }
+	c->ph_rec[k] = true;
+	return cudaEventRecord(c->ph_ev[k], st);
+}
+
 template <int BLOCK, int MINB, int SST, bool TOP, bool COUNT, bool RECORD>
 cudaError_t launch_render_t(rtx_ctx *c, const Work &w, cudaStream_t st, int blocks_per_sm)
 {
@@ -346,6 +363,7 @@ cudaError_t launch_packet(rtx_ctx *c, const Work &w, cudaStream_t st)
 		if (e != cudaSuccess) return e;
 		e = cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st);
 		if (e != cudaSuccess) return e;
+		if ((e = phase_mark(c, st, RTX_PHASE_OVERFLOW)) != cudaSuccess) return e;
 		return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 2>(c, w, st);
 	}
 	return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 0>(c, w, st);
@@ -422,6 +440,18 @@ void launch_resize_u8(const float *src, uint32_t W, uint32_t w, uint32_t h, uint
 
 int finish_stats(rtx_ctx *c)
 {
+	if (c->phase_timing && c->ph_rec[0]) {
+		/* phase k lasts from the last mark recorded at or before k to the next recorded mark */
+		int prev = 0;
+		for (int k = 0; k < RTX_NUM_PHASES; ++k) c->phase_ms[k] = 0.0;
+		for (int k = 1; k <= RTX_NUM_PHASES; ++k) {
+			if (!c->ph_rec[k]) continue;
+			float ms = 0.f;
+			if (cudaEventElapsedTime(&ms, c->ph_ev[prev], c->ph_ev[k]) == cudaSuccess) c->phase_ms[prev] = ms;
+			prev = k;
+		}
+		for (int k = 0; k <= RTX_NUM_PHASES; ++k) c->ph_rec[k] = false;
+	}
 	if (c->ev_pending) {
 		float ms = 0.f;
 		if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->stats.kernel_ms = ms;
@@ -596,6 +626,7 @@ void rtx_destroy(rtx_ctx *c)
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	for (cudaEvent_t e : c->band_ev) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : c->ph_ev) if (e) cudaEventDestroy(e);
 	for (int k = 0; k < 2; ++k) {
 		c->r_o[k].release(); c->r_d[k].release(); c->r_f[k].release(); c->r_t[k].release();
 		if (c->r_ev_in[k]) cudaEventDestroy(c->r_ev_in[k]);
@@ -637,6 +668,7 @@ int rtx_set_tunable(rtx_ctx *c, int which, int64_t v)
 	case RTX_TUNE_FRUSTUM:
 		if (v < -1 || v > 1) return fail(c, RTX_ERR_ARG, "frustum must be -1, 0 or 1");
 		c->frustum = (int)v; break;
+	case RTX_TUNE_PHASE_TIMING: c->phase_timing = v != 0; break;
 	case RTX_TUNE_RAYS_PER_THREAD:
 		if (v != 0 && v != 1 && v != 2 && v != 4) return fail(c, RTX_ERR_ARG, "rays per thread must be 0 (refill kernel), 1, 2 or 4");
 		c->rays_per_thread = (int)v; break;
@@ -1008,6 +1040,10 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 	w.cam.jitter_seed = c->opt.jitter_seed;
 	w.cam.shading = c->opt.enable_shading ? 1 : 0;
 	w.cam.ux = w.cam.vy = nullptr;
+	const bool banded = host_dst && !c->ao && c->local_tiles > 0 && (size_t)c->W * c->H * sizeof(float) >= (16u << 20);
+	const int timing_was = c->phase_timing;
+	if (banded) c->phase_timing = 0;                   /* several passes per frame: the marks would be re-recorded */
+	CU(c, phase_mark(c, st, RTX_PHASE_TABLES));
 	if (c->ray_tables && c->opt.jitter_seed == 0) {
 		CU(c, c->d_raytab.alloc(((size_t)c->W + c->H) * sizeof(float)));
 		float *ux = c->d_raytab.as<float>(), *vy = ux + c->W;
@@ -1028,6 +1064,8 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 	w.num_units = c->local_tiles * 32u;
 	w.counter = c->d_counter.as<unsigned int>();
 	w.image = c->ext_image ? c->ext_image : c->d_image.as<float>();
+	w.rowmajor = c->ext_image && c->ext_rowmajor ? 1 : 0;
+	if (w.rowmajor && c->world > 1 && rec) return fail(c, RTX_ERR_UNSUPPORTED, "rtx_bind_output_image carries the float image only (no hit records, no ambient occlusion)");
 	w.face_id = rec ? c->d_face_id.as<uint32_t>() : nullptr;
 	w.dist = rec ? c->d_dist.as<float>() : nullptr;
 	w.hit_st = c->ao ? c->d_hit_st.as<float2>() : nullptr;
@@ -1053,9 +1091,11 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 		const uint32_t nsuper = ((c->tiles_x + RTX_SUPER - 1) / RTX_SUPER) * ((c->tiles_y + RTX_SUPER - 1) / RTX_SUPER);
 		const bool two_level = c->local_tiles >= 10000;
 		if (two_level) {
+			CU(c, phase_mark(c, st, RTX_PHASE_COLLECT_SUPER));
 			k_frustum_collect_super<<<(nsuper + 3) / 4, 128, 0, st>>>(c->sc, w, c->d_slists.as<uint32_t>());
 			CU(c, cudaGetLastError());
 		}
+		CU(c, phase_mark(c, st, RTX_PHASE_COLLECT));
 		k_frustum_collect<<<(c->local_tiles + 7) / 8, 256, 0, st>>>(c->sc, w, two_level ? c->d_slists.as<uint32_t>() : nullptr, c->d_lists.as<uint32_t>());
 		CU(c, cudaGetLastError());
 		c->stats.kernel_launches = (two_level ? 2 : 1) + table_launch;
@@ -1101,6 +1141,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 		w.tile_count = c->local_tiles;
 		w.num_units = c->local_tiles * 32u;
 	} else {
+		CU(c, phase_mark(c, st, RTX_PHASE_TRAVERSAL));
 		CU(c, launch_render(c, w, st));
 	}
 	c->stats.kernel_launches += launches_per_pass * passes;
@@ -1121,11 +1162,14 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 			CU(c, cudaGetLastError());
 			++ao_launches;
 		}
+		CU(c, phase_mark(c, st, RTX_PHASE_AO));
 		k_ambient_occlusion<<<(w.num_units + 3) / 4, 128, 0, st>>>(c->sc, w, ao);
 		CU(c, cudaGetLastError());
 		++ao_launches;
 	}
 	CU(c, cudaEventRecord(c->ev1, st));
+	CU(c, phase_mark(c, st, RTX_NUM_PHASES));
+	c->phase_timing = timing_was;
 	if (host_dst) {
 		if (nbands > 1) CU(c, cudaStreamWaitEvent(st, c->copy_done, 0));     /* `st` is done when the copies are */
 		else CU(c, cudaMemcpyAsync(host_dst, w.image, frame_bytes, cudaMemcpyDeviceToHost, st));
@@ -1138,6 +1182,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 	c->rendered = true;
 	c->full_valid = false;
 	c->u8_valid = false;
+	c->ext_u8 = nullptr;
 	return RTX_OK;
 }
 
@@ -1201,6 +1246,19 @@ int rtx_bind_output(rtx_ctx *c, void *device_ptr, size_t count)
 	const size_t need = c->world > 1 ? (size_t)c->tiles_per_rank * RTX_TILE * RTX_TILE : (size_t)c->W * c->H;
 	if (device_ptr && count < need) return fail(c, RTX_ERR_ARG, "bound output is smaller than this context's share of the image");
 	c->ext_image = static_cast<float *>(device_ptr);
+	c->ext_rowmajor = false;
+	c->rendered = false;
+	return RTX_OK;
+}
+
+/* Render this rank's tiles straight into the WHOLE row-major image, wherever the kernel can address it: rank 0's
+ * device memory mapped over NVLink (rtx_peer_open) or page-locked host memory (rtx_host_register).  The pixels leave
+ * the SM as they are shaded, so the transfer overlaps the tracing tile by tile and needs no kernel of its own. */
+int rtx_bind_output_image(rtx_ctx *c, void *image_f32)
+{
+	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
+	c->ext_image = static_cast<float *>(image_f32);
+	c->ext_rowmajor = image_f32 != nullptr;
 	c->rendered = false;
 	return RTX_OK;
 }
@@ -1242,6 +1300,7 @@ int rtx_resize_u8_async(rtx_ctx *c, void *d_tiles_u8, size_t count, void *stream
 {
 	if (!c) return fail(nullptr, RTX_ERR_ARG, "null context");
 	if (!c->rendered) return fail(c, RTX_ERR_STATE, "resize before render");
+	if (c->world > 1 && c->ext_image && c->ext_rowmajor) return fail(c, RTX_ERR_STATE, "this rank's tiles went straight into a whole-image binding (rtx_bind_output_image); there is no compact tile buffer to read");
 	const uint32_t n = super_n(c), w = c->opt.width, h = c->opt.height;
 	if (n == 0 || (uint64_t)w * n > c->W || (uint64_t)h * n > c->H) return fail(c, RTX_ERR_ARG, "image smaller than width*n x height*n");
 	CU(c, cudaSetDevice(c->device));
@@ -1284,10 +1343,10 @@ int rtx_deinterleave_u8_async(rtx_ctx *c, const void *d_gathered, uint32_t world
 int rtx_download_u8(rtx_ctx *c, unsigned char *image)
 {
 	if (!c || !image) return fail(c, RTX_ERR_ARG, "null argument");
-	if (c->u8_valid) {          /* already resized on the device (rtx_resize_u8_async / rtx_deinterleave_u8_async) */
+	if (c->u8_valid) {          /* already resized on the device (rtx_resize_u8_async / rtx_deinterleave_u8_async / rtx_adopt_u8) */
 		CU(c, cudaSetDevice(c->device));
 		CU(c, cudaDeviceSynchronize());
-		CU(c, cudaMemcpy(image, c->d_u8.p, (size_t)c->opt.width * c->opt.height, cudaMemcpyDeviceToHost));
+		CU(c, cudaMemcpy(image, c->ext_u8 ? (const void *)c->ext_u8 : c->d_u8.p, (size_t)c->opt.width * c->opt.height, cudaMemcpyDeviceToHost));
 		return RTX_OK;
 	}
 	const float *src = full_image(c);
@@ -1302,6 +1361,151 @@ int rtx_download_u8(rtx_ctx *c, unsigned char *image)
 	CU(c, cudaGetLastError());
 	CU(c, cudaMemcpyAsync(image, c->d_u8.p, (size_t)w * h, cudaMemcpyDeviceToHost, c->stream));
 	CU(c, cudaStreamSynchronize(c->stream));
+	return RTX_OK;
+}
+
+/* ---- direct stores: a rank's share written straight into the final image, wherever it lives ---- */
+
+int rtx_resize_u8_to_async(rtx_ctx *c, void *image_u8, void *stream)
+{
+	if (!c || !image_u8) return fail(c, RTX_ERR_ARG, "null argument");
+	if (!c->rendered) return fail(c, RTX_ERR_STATE, "resize before render");
+	if (c->world > 1 && c->ext_image && c->ext_rowmajor) return fail(c, RTX_ERR_STATE, "this rank's tiles went straight into a whole-image binding (rtx_bind_output_image); there is no compact tile buffer to read");
+	const uint32_t n = super_n(c), w = c->opt.width, h = c->opt.height;
+	if (n == 0 || RTX_TILE % n != 0) return fail(c, RTX_ERR_UNSUPPORTED, "sqrt(n_super_samples) must divide 32");
+	if ((uint64_t)w * n > c->W || (uint64_t)h * n > c->H) return fail(c, RTX_ERR_ARG, "image smaller than width*n x height*n");
+	CU(c, cudaSetDevice(c->device));
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	if (c->world == 1) {          /* the whole frame is here, row-major */
+		const float *src = c->ext_image ? c->ext_image : c->d_image.as<float>();
+		const dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+		launch_resize_u8(src, c->W, w, h, n, static_cast<unsigned char *>(image_u8), grid, block, st);
+		CU(c, cudaGetLastError());
+		return RTX_OK;
+	}
+	const uint32_t m = RTX_TILE / n;
+	const bool quads = (m & 3u) == 0 && (w & 3u) == 0;
+	const size_t work = (size_t)c->local_tiles * (quads ? m / 4 : m) * m;
+	if (work == 0) return RTX_OK;
+	const float *src = c->ext_image ? c->ext_image : c->d_image.as<float>();
+	k_resize_tiles_u8_to<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(src, c->local_tiles, n, c->rank, c->world, c->tiles_x, w, h,
+	                                                                       static_cast<unsigned char *>(image_u8));
+	CU(c, cudaGetLastError());
+	return RTX_OK;
+}
+
+int rtx_store_tiles_async(rtx_ctx *c, void *image_f32, void *stream)
+{
+	if (!c || !image_f32) return fail(c, RTX_ERR_ARG, "null argument");
+	if (!c->rendered) return fail(c, RTX_ERR_STATE, "store before render");
+	if (c->world > 1 && c->ext_image && c->ext_rowmajor) return fail(c, RTX_ERR_STATE, "this rank's tiles went straight into a whole-image binding (rtx_bind_output_image); there is no compact tile buffer to read");
+	CU(c, cudaSetDevice(c->device));
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	const float *src = c->ext_image ? c->ext_image : c->d_image.as<float>();
+	if (c->world == 1) {
+		CU(c, cudaMemcpyAsync(image_f32, src, (size_t)c->W * c->H * sizeof(float), cudaMemcpyDefault, st));
+		return RTX_OK;
+	}
+	if (c->local_tiles == 0) return RTX_OK;
+	k_store_tiles<<<c->local_tiles, 256, 0, st>>>(src, c->local_tiles, c->rank, c->world, c->tiles_x, c->W, c->H, static_cast<float *>(image_f32));
+	CU(c, cudaGetLastError());
+	return RTX_OK;
+}
+
+int rtx_adopt_u8(rtx_ctx *c, const void *d_image_u8)
+{
+	if (!c || !d_image_u8) return fail(c, RTX_ERR_ARG, "null argument");
+	c->ext_u8 = static_cast<const unsigned char *>(d_image_u8);
+	c->u8_valid = true;
+	return RTX_OK;
+}
+
+/* Device memory another process can map (CUDA IPC): rank 0 allocates the final image and hands the 64-byte handle to
+ * the other ranks (any transport: torch.distributed, a pipe, a file); they open it and pass the pointer to
+ * rtx_resize_u8_to_async / rtx_store_tiles_async.  Peer access rides NVLink / NVSwitch. */
+int rtx_peer_alloc(rtx_ctx *c, size_t bytes, void **device_ptr, unsigned char handle[64])
+{
+	if (!c || !device_ptr || !handle || bytes == 0) return fail(c, RTX_ERR_ARG, "bad argument");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+	CU(c, cudaSetDevice(c->device));
+	void *p = nullptr;
+	CU(c, cudaMalloc(&p, bytes));
+	cudaError_t e = cudaMemset(p, 0, bytes);
+	cudaIpcMemHandle_t h;
+	if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+	if (e != cudaSuccess) { cudaFree(p); return cuda_fail(c, e, "cudaIpcGetMemHandle"); }
+	std::memcpy(handle, &h, 64);
+	*device_ptr = p;
+	return RTX_OK;
+}
+
+int rtx_peer_open(rtx_ctx *c, const unsigned char handle[64], void **device_ptr)
+{
+	if (!c || !device_ptr || !handle) return fail(c, RTX_ERR_ARG, "bad argument");
+	CU(c, cudaSetDevice(c->device));
+	cudaIpcMemHandle_t h;
+	std::memcpy(&h, handle, 64);
+	void *p = nullptr;
+	CU(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	*device_ptr = p;
+	return RTX_OK;
+}
+
+int rtx_peer_close(rtx_ctx *c, void *device_ptr)
+{
+	if (!c || !device_ptr) return fail(c, RTX_ERR_ARG, "bad argument");
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaIpcCloseMemHandle(device_ptr));
+	return RTX_OK;
+}
+
+int rtx_peer_free(rtx_ctx *c, void *device_ptr)
+{
+	if (!c || !device_ptr) return fail(c, RTX_ERR_ARG, "bad argument");
+	CU(c, cudaSetDevice(c->device));
+	if (c->ext_u8 == device_ptr) { c->ext_u8 = nullptr; c->u8_valid = false; }
+	CU(c, cudaFree(device_ptr));
+	return RTX_OK;
+}
+
+/* Page-lock caller-owned host memory (e.g. a shared mapping that several rank processes opened) and map it into the
+ * device's address space; *device_alias is what kernels of this process may write (== p under unified addressing). */
+int rtx_host_register(void *p, size_t bytes, void **device_alias)
+{
+	if (!p || bytes == 0) return fail(nullptr, RTX_ERR_ARG, "bad argument");
+	cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+	if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostRegister");
+	void *d = nullptr;
+	e = cudaHostGetDevicePointer(&d, p, 0);
+	if (e != cudaSuccess) { cudaHostUnregister(p); return cuda_fail(nullptr, e, "cudaHostGetDevicePointer"); }
+	if (device_alias) *device_alias = d;
+	return RTX_OK;
+}
+
+int rtx_host_unregister(void *p)
+{
+	if (!p) return fail(nullptr, RTX_ERR_ARG, "null pointer");
+	cudaError_t e = cudaHostUnregister(p);
+	if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostUnregister");
+	return RTX_OK;
+}
+
+/* Blocking copy of raw device memory (e.g. a buffer of rtx_peer_alloc) to the host, after everything queued on the device. */
+int rtx_copy_to_host(rtx_ctx *c, void *host_dst, const void *device_src, size_t bytes)
+{
+	if (!c || !host_dst || !device_src) return fail(c, RTX_ERR_ARG, "null argument");
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaDeviceSynchronize());
+	CU(c, cudaMemcpy(host_dst, device_src, bytes, cudaMemcpyDeviceToHost));
+	return RTX_OK;
+}
+
+int rtx_phase_ms(const rtx_ctx *c, double *ms)
+{
+	if (!c || !ms) return fail(nullptr, RTX_ERR_ARG, "null argument");
+	rtx_ctx *m = const_cast<rtx_ctx *>(c);
+	if (m->ev_pending && cudaEventQuery(m->ev1) == cudaSuccess) finish_stats(m);
+	for (int k = 0; k < RTX_NUM_PHASES; ++k) ms[k] = c->phase_ms[k];
 	return RTX_OK;
 }
 

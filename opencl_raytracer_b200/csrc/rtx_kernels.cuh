@@ -297,6 +297,8 @@ struct Work {
 	uint32_t num_units;          /* tile_count * 32 */
 	unsigned int *counter;       /* persistent-kernel work counter (zeroed before launch) */
 	float *image;                /* world == 1: row-major W x H; else compact [local_tile][32][32] */
+	int rowmajor;                /* world > 1: `image` is the whole row-major W x H image (a peer's or mapped host memory,
+	                                rtx_bind_output_image) and this rank writes only the pixels of its own tiles */
 	uint32_t *face_id;           /* optional (record mode), same indexing as image */
 	float *dist;
 	float2 *hit_st;              /* optional (ambient occlusion): parametric coordinates of the hit */
@@ -315,7 +317,7 @@ RTX_DEV bool unit_pixel(const Work &w, uint32_t unit, uint32_t lane, uint32_t &x
 	const uint32_t px = ((sub & 3u) << 3) + (lane & 7u), py = ((sub >> 2) << 2) + (lane >> 3);
 	x = tx * RTX_TILE + px;
 	y = ty * RTX_TILE + py;
-	out = w.world > 1 ? (size_t)ltile * (RTX_TILE * RTX_TILE) + py * RTX_TILE + px : (size_t)y * w.cam.W + x;
+	out = (w.world > 1 && !w.rowmajor) ? (size_t)ltile * (RTX_TILE * RTX_TILE) + py * RTX_TILE + px : (size_t)y * w.cam.W + x;
 	return ty < w.tiles_y && x < w.cam.W && y < w.cam.H;
 }
 
@@ -796,7 +798,7 @@ k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 		for (int r = 0; r < NR; ++r) {
 			const uint32_t px = px0 + (r % RX), py = py0 + (r / RX);
 			const uint32_t x = tx * RTX_TILE + px, y = ty * RTX_TILE + py;
-			out[r] = w.world > 1 ? (size_t)ltile * (RTX_TILE * RTX_TILE) + py * RTX_TILE + px : (size_t)y * w.cam.W + x;
+			out[r] = (w.world > 1 && !w.rowmajor) ? (size_t)ltile * (RTX_TILE * RTX_TILE) + py * RTX_TILE + px : (size_t)y * w.cam.W + x;
 			best[r].dist = __int_as_float(0x7f800000); best[r].tri = 0xffffffffu; best[r].s = best[r].t = 0.f;
 			d[r] = primary_dir(w.cam, x, y);
 			if (ty < w.tiles_y && x < w.cam.W && y < w.cam.H) {
@@ -1476,6 +1478,82 @@ __global__ void k_resize_tiles_u8(const float *__restrict__ tiles, uint32_t ntil
 				total = rn_add(total, src[(oy * n + sy) * RTX_TILE + (ox * n + sx)]);
 	}
 	out[i] = (unsigned char)(int)rn_mul(rn_div(total, (float)(n * n)), 255.0f);
+}
+
+/* RayTracer::resize of a rank's compact tiles written STRAIGHT into a row-major width x height byte image -- the
+ * rank's own, or rank 0's mapped through NVLink peer memory (rtx_peer_open): resize + gather + de-interleave of the
+ * byte path in one kernel, no collective.  One thread per output pixel, or per 4 adjacent ones when they can leave as
+ * one aligned 32-bit store (peer stores of single bytes cost a 32-byte sector each).  Same summation order as
+ * k_resize_u8 (ray_tracer.cc:3-15). */
+RTX_DEV unsigned char resize_one(const float *__restrict__ src, uint32_t oy, uint32_t ox, uint32_t n)
+{
+	float total = 0.0f;
+	if (n == 4) {
+#pragma unroll
+		for (uint32_t sy = 0; sy < 4; ++sy) {
+			const float4 v = __ldcs(reinterpret_cast<const float4 *>(src + (oy * 4 + sy) * RTX_TILE + ox * 4));
+			total = rn_add(rn_add(rn_add(rn_add(total, v.x), v.y), v.z), v.w);
+		}
+	} else {
+		for (uint32_t sy = 0; sy < n; ++sy)
+			for (uint32_t sx = 0; sx < n; ++sx)
+				total = rn_add(total, src[(oy * n + sy) * RTX_TILE + (ox * n + sx)]);
+	}
+	return (unsigned char)(int)rn_mul(rn_div(total, (float)(n * n)), 255.0f);
+}
+
+__global__ void k_resize_tiles_u8_to(const float *__restrict__ tiles, uint32_t local_tiles, uint32_t n, uint32_t rank, uint32_t world,
+                                     uint32_t tiles_x, uint32_t width, uint32_t height, unsigned char *__restrict__ image)
+{
+	const uint32_t m = RTX_TILE / n;                 /* output pixels per tile side */
+	const bool quads = (m & 3u) == 0 && (width & 3u) == 0 && (reinterpret_cast<uintptr_t>(image) & 3u) == 0 &&
+	                   (reinterpret_cast<uintptr_t>(tiles) & 15u) == 0;
+	const uint32_t per_row = quads ? m / 4 : m, per_tile = per_row * m;
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (size_t)local_tiles * per_tile) return;
+	const uint32_t lt = (uint32_t)(i / per_tile), r = (uint32_t)(i % per_tile), oy = r / per_row, oq = r % per_row;
+	const uint32_t tile = lt * world + rank, tx = tile % tiles_x, ty = tile / tiles_x;
+	const float *src = tiles + (size_t)lt * (RTX_TILE * RTX_TILE);
+	const uint32_t y = ty * m + oy;
+	if (y >= height) return;
+	if (quads) {
+		const uint32_t x = tx * m + oq * 4;
+		if (x >= width) return;                      /* width % 4 == 0: a quad is inside or outside as a whole */
+		uchar4 v;
+		v.x = resize_one(src, oy, oq * 4, n); v.y = resize_one(src, oy, oq * 4 + 1, n);
+		v.z = resize_one(src, oy, oq * 4 + 2, n); v.w = resize_one(src, oy, oq * 4 + 3, n);
+		*reinterpret_cast<uchar4 *>(image + (size_t)y * width + x) = v;
+	} else {
+		const uint32_t x = tx * m + oq;
+		if (x < width) image[(size_t)y * width + x] = resize_one(src, oy, oq, n);
+	}
+}
+
+/* A rank's compact float tiles written straight into a row-major W x H float image that the kernel can address: the
+ * rank's own, a peer's (rtx_peer_open: the float gather without a collective), or page-locked HOST memory mapped into
+ * the device (rtx_host_register: every rank's tiles leave over its own PCIe link).  One CTA per tile, 128-bit stores
+ * (a tile row = 128 contiguous bytes). */
+__global__ void __launch_bounds__(256)
+k_store_tiles(const float *__restrict__ tiles, uint32_t local_tiles, uint32_t rank, uint32_t world, uint32_t tiles_x,
+              uint32_t W, uint32_t H, float *__restrict__ image)
+{
+	const uint32_t lt = blockIdx.x;
+	if (lt >= local_tiles) return;
+	const uint32_t tile = lt * world + rank, tx = tile % tiles_x, ty = tile / tiles_x;
+	const float *src = tiles + (size_t)lt * (RTX_TILE * RTX_TILE);
+	const uint32_t x0 = tx * RTX_TILE, y0 = ty * RTX_TILE;
+	const bool vec = (W & 3u) == 0 && (reinterpret_cast<uintptr_t>(image) & 15u) == 0 && (reinterpret_cast<uintptr_t>(tiles) & 15u) == 0;
+	if (vec) {
+		const uint32_t py = threadIdx.x >> 3, px = (threadIdx.x & 7u) << 2;
+		if (y0 + py < H && x0 + px < W)              /* W % 4 == 0: four pixels are inside or outside together */
+			__stcs(reinterpret_cast<float4 *>(image + (size_t)(y0 + py) * W + x0 + px),
+			       __ldcs(reinterpret_cast<const float4 *>(src + py * RTX_TILE + px)));
+	} else {
+		for (uint32_t i = threadIdx.x; i < RTX_TILE * RTX_TILE; i += blockDim.x) {
+			const uint32_t px = i & 31u, py = i >> 5;
+			if (x0 + px < W && y0 + py < H) image[(size_t)(y0 + py) * W + x0 + px] = src[i];
+		}
+	}
 }
 
 /* rank-major gathered compact u8 tiles -> row-major width x height byte image (rank 0) */

@@ -20,13 +20,14 @@ import numpy as np
 from .scene import Scene
 
 _LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-LIB_PATH = os.path.join(_LIBDIR, "librtx_b200.so")
+LIB_PATH = os.environ.get("RTX_B200_LIB") or os.path.join(_LIBDIR, "librtx_b200.so")     # override: A/B builds of the kernels
 
 NO_HIT = 0xFFFFFFFF
 
 OK, ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NOMEM = range(7)
 
-TUNE_KERNEL, TUNE_LEAF_SIZE, TUNE_RECORD_HITS, TUNE_COUNTERS, TUNE_TOP_SMEM, TUNE_BLOCKS_PER_SM, TUNE_FLATTEN_ON_DEVICE, TUNE_RAYS_PER_THREAD, TUNE_FRUSTUM, TUNE_LIST_RAYS_PER_THREAD, TUNE_INCOHERENT_KERNEL, TUNE_RAY_TABLES = range(1, 13)
+TUNE_KERNEL, TUNE_LEAF_SIZE, TUNE_RECORD_HITS, TUNE_COUNTERS, TUNE_TOP_SMEM, TUNE_BLOCKS_PER_SM, TUNE_FLATTEN_ON_DEVICE, TUNE_RAYS_PER_THREAD, TUNE_FRUSTUM, TUNE_LIST_RAYS_PER_THREAD, TUNE_INCOHERENT_KERNEL, TUNE_RAY_TABLES, TUNE_PHASE_TIMING = range(1, 14)
+PHASES = ("tables", "collect_super", "collect", "traversal", "overflow", "ao")     # RTX_PHASE_* of include/rtx_b200.h
 KERNEL_PERSISTENT, KERNEL_EXHAUSTIVE = 0, 1
 
 # every symbol include/rtx_b200.h declares (tests check the library exports them all)
@@ -37,6 +38,8 @@ ABI_SYMBOLS = (
     "rtx_trace_rays_device", "rtx_trace_random_rays", "rtx_tile_layout", "rtx_deinterleave_async", "rtx_bind_output",
     "rtx_probe_bandwidth", "rtx_resize_u8_async", "rtx_deinterleave_u8_async", "rtx_render_download",
     "rtx_upload_mesh", "rtx_download_tree", "rtx_build_stats", "rtx_download_normals",
+    "rtx_resize_u8_to_async", "rtx_store_tiles_async", "rtx_adopt_u8", "rtx_peer_alloc", "rtx_peer_open", "rtx_peer_close",
+    "rtx_peer_free", "rtx_host_register", "rtx_host_unregister", "rtx_phase_ms", "rtx_copy_to_host", "rtx_bind_output_image",
 )
 
 
@@ -150,6 +153,30 @@ def load_library():
     lib.rtx_tile_layout.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.rtx_deinterleave_async.restype = C.c_int
     lib.rtx_deinterleave_async.argtypes = [vp, vp, C.c_uint32, vp]
+    lib.rtx_resize_u8_to_async.restype = C.c_int
+    lib.rtx_resize_u8_to_async.argtypes = [vp, vp, vp]
+    lib.rtx_store_tiles_async.restype = C.c_int
+    lib.rtx_store_tiles_async.argtypes = [vp, vp, vp]
+    lib.rtx_adopt_u8.restype = C.c_int
+    lib.rtx_adopt_u8.argtypes = [vp, vp]
+    lib.rtx_peer_alloc.restype = C.c_int
+    lib.rtx_peer_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    lib.rtx_peer_open.restype = C.c_int
+    lib.rtx_peer_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.rtx_peer_close.restype = C.c_int
+    lib.rtx_peer_close.argtypes = [vp, vp]
+    lib.rtx_peer_free.restype = C.c_int
+    lib.rtx_peer_free.argtypes = [vp, vp]
+    lib.rtx_host_register.restype = C.c_int
+    lib.rtx_host_register.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.rtx_host_unregister.restype = C.c_int
+    lib.rtx_host_unregister.argtypes = [vp]
+    lib.rtx_bind_output_image.restype = C.c_int
+    lib.rtx_bind_output_image.argtypes = [vp, vp]
+    lib.rtx_copy_to_host.restype = C.c_int
+    lib.rtx_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.rtx_phase_ms.restype = C.c_int
+    lib.rtx_phase_ms.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -379,6 +406,10 @@ class CudaHost:
     def bind_output(self, device_ptr: int, count: int):
         self._ck(self._lib.rtx_bind_output(self._ctx, C.c_void_p(device_ptr), count))
 
+    def bind_output_image(self, image_f32: int):
+        """tile_world > 1: render this rank's tiles straight into the whole row-major float image (peer / mapped host memory)."""
+        self._ck(self._lib.rtx_bind_output_image(self._ctx, C.c_void_p(image_f32)))
+
     def trace_rays(self, origins, dirs, max_distance: float = 100000.0, out_face_id=None, out_distance=None):
         """Closest hits of host rays (4 floats per origin / direction).  Page-locked inputs AND outputs let the chunks
         of a large batch overlap their copies with the tracing (rtx_trace_rays)."""
@@ -415,6 +446,57 @@ class CudaHost:
 
     def deinterleave_async(self, d_gathered: int, world: int, stream: int = 0):
         self._ck(self._lib.rtx_deinterleave_async(self._ctx, C.c_void_p(d_gathered), world, C.c_void_p(stream)))
+
+    # -- direct stores: this rank's share straight into the final image (own / peer / mapped host memory) --
+    def resize_u8_to_async(self, image_u8: int, stream: int = 0):
+        self._ck(self._lib.rtx_resize_u8_to_async(self._ctx, C.c_void_p(image_u8), C.c_void_p(stream)))
+
+    def store_tiles_async(self, image_f32: int, stream: int = 0):
+        self._ck(self._lib.rtx_store_tiles_async(self._ctx, C.c_void_p(image_f32), C.c_void_p(stream)))
+
+    def adopt_u8(self, d_image_u8: int):
+        self._ck(self._lib.rtx_adopt_u8(self._ctx, C.c_void_p(d_image_u8)))
+
+    def peer_alloc(self, nbytes: int):
+        """(device pointer, 64-byte IPC handle) of fresh device memory other rank processes can map."""
+        p, h = C.c_void_p(), C.create_string_buffer(64)
+        self._ck(self._lib.rtx_peer_alloc(self._ctx, nbytes, C.byref(p), h))
+        return p.value, h.raw
+
+    def peer_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._ck(self._lib.rtx_peer_open(self._ctx, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def peer_close(self, ptr: int):
+        self._ck(self._lib.rtx_peer_close(self._ctx, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int):
+        self._ck(self._lib.rtx_peer_free(self._ctx, C.c_void_p(ptr)))
+
+    def copy_to_host(self, out: np.ndarray, device_ptr: int) -> np.ndarray:
+        assert out.flags.c_contiguous
+        self._ck(self._lib.rtx_copy_to_host(self._ctx, C.c_void_p(out.ctypes.data), C.c_void_p(device_ptr), out.nbytes))
+        return out
+
+    def phase_ms(self) -> dict:
+        """Device time per launch group of the last frame (needs TUNE_PHASE_TIMING)."""
+        ms = (C.c_double * len(PHASES))()
+        self._ck(self._lib.rtx_phase_ms(self._ctx, ms))
+        return dict(zip(PHASES, [float(x) for x in ms]))
+
+
+def host_register(array: np.ndarray) -> int:
+    """Page-lock a host array (e.g. a shared mapping) and map it into the device; returns the pointer kernels may write."""
+    lib = load_library()
+    d = C.c_void_p()
+    _check(lib, None, lib.rtx_host_register(C.c_void_p(array.ctypes.data), array.nbytes, C.byref(d)))
+    return d.value
+
+
+def host_unregister(array: np.ndarray) -> None:
+    lib = load_library()
+    _check(lib, None, lib.rtx_host_unregister(C.c_void_p(array.ctypes.data)))
 
 
 def write_pgm(path: str, image_u8: np.ndarray) -> None:

@@ -3,14 +3,22 @@
 The scene is replicated; the super-sampled image is cut into 32x32-pixel tiles
 and tile ``t`` is rendered by rank ``t % world`` (interleaved, so sky and
 geometry are spread evenly).  Each rank's kernel writes its tiles into a compact
-``[local_tile][32][32]`` float buffer owned by torch; the only communication of a
-frame is ONE ``torch.distributed.gather`` of those buffers to rank 0 (NCCL over
-NVLink on the GPU box, gloo on CPU in the tests), followed on rank 0 by a
-de-interleave kernel into the row-major image that ``download`` returns.
-``world == 1`` skips the collective entirely.
+``[local_tile][32][32]`` float buffer owned by torch.  How the frame reaches rank 0
+is the ``gather`` mode of ``TiledRenderer``:
 
-``torch`` is plumbing here (device memory, streams, the process group); tracing
-and de-interleaving go through the C ABI (include/rtx_b200.h).
+* ``"float"`` / ``"u8"``: ONE ``torch.distributed.gather`` (NCCL over NVLink on the GPU
+  box, gloo on CPU in the tests) of the float tiles -- or of the bytes after every rank
+  applied ``RayTracer::resize`` to its own tiles --, then a de-interleave kernel on rank 0;
+* ``"p2p_u8"`` / ``"p2p_float"``: no collective on the data path.  Rank 0's final image
+  is mapped into every rank process (CUDA IPC) and each rank's resize / store kernel
+  writes its share straight into it over NVLink; a one-element all-reduce orders the ranks.
+
+``SharedHostImage`` is the same idea for the caller's HOST image: one page-locked buffer
+mapped by every rank, so each rank's tiles leave over its own PCIe link.
+``world == 1`` skips all communication.
+
+``torch`` is plumbing here (device memory, streams, the process group); tracing,
+resizing, storing and de-interleaving go through the C ABI (include/rtx_b200.h).
 """
 from __future__ import annotations
 
@@ -77,18 +85,30 @@ class TiledRenderer:
         r = TiledRenderer(rt, scene, rank, world, device)
         r.render_frame()                # kernel -> (gather -> de-interleave on rank 0), all on torch's stream
         img = r.download()              # rank 0 only
+
+    gather (what a frame ends with on rank 0, and how it gets there):
+      "float"      ONE NCCL gather of the float tiles + de-interleave kernel: the image ``download(float*)`` returns
+      "u8"         every rank applies RayTracer::resize to its own tiles, ONE NCCL gather of the bytes + de-interleave
+                   ((n*n*4)x less traffic into rank 0; needs sqrt(nSuperSamples) to divide 32)
+      "p2p_u8"     no collective on the data path: every rank's resize kernel stores its bytes straight into rank 0's
+                   final image through NVLink peer memory (CUDA IPC mapping, set up once); the frame ends with a
+                   one-element all-reduce on the same stream, which completes on rank 0 only when every rank's store
+                   kernel has finished.  Two images alternate, so rank 0 may read frame k while frame k+1 is written.
+      "p2p_float"  the float image: every rank's traversal kernel writes its pixels straight into rank 0's row-major
+                   image (rtx_bind_output_image on the peer mapping), so the transfer overlaps the tracing; same rendezvous
     """
 
     def __init__(self, rt, scene, rank: int, world: int, device: int, jitter_seed: int = 0, gather: str = "float"):
-        """gather = "float": the frame's collective moves the float tiles (what ``download(float*)`` needs);
-        gather = "u8": every rank applies RayTracer::resize to its own tiles first and the collective moves
-        bytes -- (n*n*4)x less traffic into rank 0; needs sqrt(nSuperSamples) to divide 32."""
         import torch
         from . import host
         self.torch = torch
         self.rank, self.world, self.rt = rank, world, rt
+        if world == 1 and gather.startswith("p2p_"):
+            gather = gather[4:]
         self.gather = gather
-        if gather == "u8" and world > 1 and TILE % rt.n != 0:
+        if gather not in ("float", "u8", "p2p_u8", "p2p_float"):
+            raise ValueError("unknown gather mode %r" % gather)
+        if gather.endswith("u8") and world > 1 and TILE % rt.n != 0:
             raise ValueError("u8 gather needs sqrt(nSuperSamples) to divide %d" % TILE)
         self.dev = torch.device("cuda", device)
         self.host = host.CudaHost(rt, device=device, jitter_seed=jitter_seed, tile_rank=rank, tile_world=world)
@@ -98,15 +118,58 @@ class TiledRenderer:
         self.host.bind_output(self.local.data_ptr(), n)
         self.gathered = None
         self.kernel_launches = 0
+        self.frame = 0
+        self.timing = False          # record torch events around the multi-GPU phases (phase_ms)
+        self._ev = None
+        self.peer = None             # p2p modes: the two final images in rank 0's memory, as seen from this rank
         if gather == "u8" and world > 1:
             m = TILE // rt.n
             self.local_u8 = torch.zeros(tile_counts(rt.totalWidth, rt.totalHeight, world)[2] * m * m, dtype=torch.uint8, device=self.dev)
+        if gather.startswith("p2p_"):
+            import torch.distributed as dist
+            nbytes = rt.options.width * rt.options.height if gather == "p2p_u8" else rt.totalWidth * rt.totalHeight * 4
+            # collective set-up that cannot leave a rank waiting: every step ends with all ranks knowing whether it worked
+            box, err = [None], None
+            if rank == 0:
+                try:
+                    owned = [self.host.peer_alloc(nbytes) for _ in range(2)]
+                    box = [[h for _, h in owned]]
+                    self.peer = [p for p, _ in owned]
+                except host.RtxError as e:
+                    err = str(e)
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0 and box[0] is not None:
+                try:
+                    self.peer = [self.host.peer_open(h) for h in box[0]]
+                except host.RtxError as e:
+                    err = str(e)
+            ok = torch.tensor([0 if (err or box[0] is None) else 1], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if self.peer and rank == 0:
+                    for p in self.peer:
+                        self.host.peer_free(p)
+                self.peer = None
+                self.host.close()
+                raise RuntimeError("peer-memory gather unavailable on this box (rank %d: %s)" % (rank, err or "another rank failed"))
+            self.flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+
+    def _mark(self, name):
+        if self.timing:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._ev.append((name, e))
 
     def render_frame(self):
         torch = self.torch
         stream = torch.cuda.current_stream(self.dev).cuda_stream
+        if self.timing:
+            self._ev = []
+        if self.gather == "p2p_float":       # the pixels go straight into rank 0's image as they are shaded
+            self.host.bind_output_image(self.peer[self.frame & 1])
         self.host.render_async(stream)
         self.kernel_launches += self.host.last_launches()
+        self._mark("resize")
         if self.gather == "u8":
             if self.world == 1:
                 self.host.resize_u8_async(0, 0, stream)
@@ -114,19 +177,47 @@ class TiledRenderer:
             else:
                 self.host.resize_u8_async(self.local_u8.data_ptr(), self.local_u8.numel(), stream)
                 self.kernel_launches += 1
+                self._mark("gather")
                 self.gathered = gather_to_rank0(self.local_u8, self.world, self.rank)
+                self._mark("deinterleave")
                 if self.rank == 0:
                     self.host.deinterleave_u8_async(self.gathered.data_ptr(), self.world, stream)
                     self.kernel_launches += 1
-        elif self.world > 1:
+        elif self.gather == "float" and self.world > 1:
+            self._mark("gather")
             self.gathered = gather_to_rank0(self.local, self.world, self.rank)
+            self._mark("deinterleave")
             if self.rank == 0:
                 self.host.deinterleave_async(self.gathered.data_ptr(), self.world, stream)
                 self.kernel_launches += 1
+        elif self.gather.startswith("p2p_"):
+            import torch.distributed as dist
+            target = self.peer[self.frame & 1]
+            if self.gather == "p2p_u8":
+                self.host.resize_u8_to_async(target, stream)      # resize + store into rank 0's image, one kernel
+                self.kernel_launches += 1
+            self._mark("gather")
+            dist.all_reduce(self.flag)                            # rendezvous: every rank's stores have landed
+            if self.rank == 0 and self.gather == "p2p_u8":
+                self.host.adopt_u8(target)
+            self.last_target = target
+        self._mark("end")
+        self.frame += 1
+
+    def phase_ms(self):
+        """Device time per phase of the last frame rendered with ``timing`` (and TUNE_PHASE_TIMING) set: the launch groups
+        of rtx_render_async (host.PHASES) + resize / gather / deinterleave of this module.  Call after a synchronize."""
+        out = dict(self.host.phase_ms())
+        ev = self._ev or []
+        for (name, a), (_, b) in zip(ev, ev[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
 
     def download(self):
         assert self.rank == 0
         self.torch.cuda.synchronize(self.dev)
+        if self.gather == "p2p_float":
+            return self.host.copy_to_host(np.empty((self.rt.totalHeight, self.rt.totalWidth), np.float32), self.last_target)
         return self.host.download()
 
     def download_u8(self):
@@ -135,4 +226,66 @@ class TiledRenderer:
         return self.host.download_u8()
 
     def close(self):
+        if self.peer:
+            self.torch.cuda.synchronize(self.dev)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.barrier()                        # nobody unmaps or frees while a peer may still store
+            if self.rank == 0:
+                for p in self.peer:
+                    self.host.peer_free(p)
+            else:
+                for p in self.peer:
+                    self.host.peer_close(p)
+            self.peer = None
         self.host.close()
+
+
+class SharedHostImage:
+    """The caller's float image as ONE page-locked host buffer that every rank process maps (a file in /dev/shm) and
+    registers with CUDA: each rank's tiles then leave the device over that rank's own PCIe link
+    (rtx_store_tiles_async with the mapped pointer) instead of funnelling through rank 0's.  Collective constructor."""
+
+    def __init__(self, rt, rank: int, world: int, directory: str = "/dev/shm"):
+        import os
+        import torch.distributed as dist
+        from . import host
+        self.host_mod, self.rank = host, rank
+        shape = (rt.totalHeight, rt.totalWidth)
+        box = [None]
+        self.array = None
+        if rank == 0:
+            self.path = os.path.join(directory, "rtx_b200_image_%d_%d" % (os.getpid(), id(self) & 0xffff))
+            try:
+                fd = os.open(self.path, os.O_CREAT | os.O_RDWR, 0o600)
+                try:
+                    os.posix_fallocate(fd, 0, shape[0] * shape[1] * 4)     # ENOSPC here, not SIGBUS at the first store
+                finally:
+                    os.close(fd)
+                self.array = np.memmap(self.path, dtype=np.float32, mode="r+", shape=shape)
+                box = [self.path]
+            except OSError as e:
+                try:
+                    os.unlink(self.path)
+                except OSError:
+                    pass
+                box = [None]
+                self.error = str(e)
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        if box[0] is None:
+            raise RuntimeError("no room for the shared host image in %s: %s" % (directory, getattr(self, "error", "rank 0 failed")))
+        if rank != 0:
+            self.path = box[0]
+            self.array = np.memmap(self.path, dtype=np.float32, mode="r+", shape=shape)
+        self.array[::1024] = 0            # touch: the pages exist before they are pinned
+        self.device_ptr = host.host_register(self.array)
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            os.unlink(self.path)          # the mappings keep it alive
+
+    def close(self):
+        if self.array is not None:
+            self.host_mod.host_unregister(self.array)
+            self.array = None

@@ -463,6 +463,68 @@ def test_tile_partition_equals_single_image(po, soup_scene, world):
             c.close()
 
 
+@pytest.mark.parametrize("world,w,h_,ss", [(2, 150, 70, 4), (3, 150, 70, 4), (8, 96, 64, 16), (4, 77, 53, 1), (2, 64, 40, 64)])
+def test_direct_stores_equal_single_image(po, soup_scene, world, w, h_, ss):
+    """The collective-free paths emulated on one GPU: every rank stores its share straight into the final image
+    (rtx_resize_u8_to_async / rtx_store_tiles_async) -- device memory from rtx_peer_alloc (what the other ranks map with
+    rtx_peer_open on a multi-GPU box) and page-locked host memory mapped into the device (rtx_host_register)."""
+    host = require_gpu()
+    rt = host.RayTracer(host.Options(width=w, height=h_, nSuperSamples=ss))
+    with host.CudaHost(rt) as h:
+        h.upload_scene(soup_scene)
+        h()
+        single, single_u8 = h.download(), h.download_u8()
+    ctxs = [host.CudaHost(rt, tile_rank=r, tile_world=world) for r in range(world)]
+    shared = np.full((rt.totalHeight, rt.totalWidth), -1.0, np.float32)
+    try:
+        d_u8, handle = ctxs[0].peer_alloc(w * h_)
+        d_f32, _ = ctxs[0].peer_alloc(rt.totalWidth * rt.totalHeight * 4)
+        assert len(handle) == 64
+        alias = host.host_register(shared)
+        for c in ctxs:
+            c.upload_scene(soup_scene)
+            c()
+            c.resize_u8_to_async(d_u8)
+            c.store_tiles_async(d_f32)
+            c.store_tiles_async(alias)
+            c.synchronize()
+        ctxs[0].adopt_u8(d_u8)
+        assert np.array_equal(ctxs[0].download_u8(), single_u8)
+        assert np.array_equal(shared, single)
+        assert np.array_equal(ctxs[0].copy_to_host(np.empty_like(single), d_f32), single)
+        # ... and without any store kernel: the traversal kernel of every rank writes its pixels straight into the whole image
+        shared[:] = -1.0
+        for c in ctxs:
+            c.bind_output_image(alias)
+            c()
+            with pytest.raises(host.RtxError):
+                c.store_tiles_async(d_f32)           # no compact tile buffer exists in this mode
+            c.bind_output_image(0)
+        assert np.array_equal(shared, single)
+        host.host_unregister(shared)
+        ctxs[0].peer_free(d_u8)
+        ctxs[0].peer_free(d_f32)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_phase_timing(sibenik_scene):
+    """RTX_TUNE_PHASE_TIMING: the launch groups of a frame add up to its device time, and the frustum path names them."""
+    host = require_gpu()
+    rt = host.RayTracer(host.Options(width=1920, height=1080, nSuperSamples=4))
+    with host.CudaHost(rt) as h:
+        h.set_tunable(host.TUNE_PHASE_TIMING, 1)
+        h.upload_scene(sibenik_scene)
+        h()
+        h()
+        ph, st = h.phase_ms(), h.stats()
+        assert set(ph) == set(host.PHASES)
+        assert ph["collect"] > 0 and ph["traversal"] > 0 and ph["ao"] == 0
+        assert ph["traversal"] > 0.5 * st["kernel_ms"]
+        assert abs(sum(ph.values()) - st["kernel_ms"]) < 0.05 + 0.2 * st["kernel_ms"]
+
+
 @pytest.mark.parametrize("leaf", [1, 2, 4, 8])
 def test_device_tree_scan_equals_host_flatten(po, soup_scene, sah_scene, sibenik_scene, leaf):
     """rtx_upload validates the tree and computes the flatten's prefix counts and depth on the device (k_tree_*);
