@@ -705,27 +705,10 @@ def main():
             st = torch.cuda.current_stream(dev).cuda_stream
             timed("upload", lambda: r_float.host.upload(*np_arrs))
 
-            def go():
-                r_float.host.render_async(st)
-                r_float.host.store_tiles_async(shared.device_ptr, st)
-                torch.cuda.synchronize(dev)
-            timed("render+store", go)
-
-        def frame_shared_direct():
-            # the same, without the store kernel: the traversal kernel itself writes each pixel into the mapped host image
-            # (rtx_bind_output_image), so the PCIe transfer overlaps the tracing
-            st = torch.cuda.current_stream(dev).cuda_stream
-            timed("upload", lambda: r_float.host.upload(*np_arrs))
-
-            def go():
-                r_float.host.bind_output_image(shared.device_ptr)
-                r_float.host.render_async(st)
-                torch.cuda.synchronize(dev)
-                r_float.host.bind_output(r_float.local.data_ptr(), r_float.local.numel())
-            timed("render(into host image)", go)
+            timed("render+store", lambda: r_float.host.render_store(shared.device_ptr))
 
         res, phases = [], []
-        fns = (frame_float, frame_u8) + ((frame_pipelined,) if world == 1 else ()) + ((frame_shared, frame_shared_direct) if shared is not None else ())
+        fns = (frame_float, frame_u8) + ((frame_pipelined,) if world == 1 else ()) + ((frame_shared,) if shared is not None else ())
         for fn in fns:
             for _ in range(2):
                 fn()
@@ -751,15 +734,11 @@ def main():
             same = None
             if rank == 0:                                # the two host images must be the same image
                 same = bool(np.array_equal(np.asarray(shared.array).view(np.uint32), out_f.view(np.uint32)))
-            best = 3 if res[3] >= res[2] else 2
-            calls = ("per rank: rtx_upload + rtx_bind_output_image(host image) + rtx_render_async: the traversal kernel writes its pixels "
-                     "straight into ONE page-locked host image mapped by every rank process (multigpu.SharedHostImage, rtx_host_register)",
-                     "per rank: rtx_upload + rtx_render_async + rtx_store_tiles_async into ONE page-locked host image mapped by every "
-                     "rank process (multigpu.SharedHostImage, rtx_host_register)")
-            e2e = {"value": res[best], "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": rays * 4,
-                   "calls": calls[0 if best == 3 else 1] + ": each rank's tiles leave over its own PCIe link; wall clock incl. a barrier per frame",
-                   "phase_ms": phases[best], "identical_to_gathered_image": same,
-                   "store_kernel_variant": {"value": res[2], "phase_ms": phases[2]}, "direct_render_variant": {"value": res[3], "phase_ms": phases[3]},
+            e2e = {"value": res[2], "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": rays * 4,
+                   "calls": "per rank: rtx_upload + rtx_render_store into ONE page-locked host image mapped by every rank process "
+                            "(multigpu.SharedHostImage, rtx_host_register): the warp that finishes a tile sends it, so each rank's tiles "
+                            "leave over its own PCIe link while the rest is still being traced; wall clock incl. a barrier per frame",
+                   "phase_ms": phases[2], "identical_to_gathered_image": same,
                    "via_rank0_gather": {"value": via_gather["value"], "calls": via_gather["calls"], "phase_ms": via_gather["phase_ms"]}}
             shared.close()
         elif world > 1:

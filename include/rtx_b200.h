@@ -256,6 +256,9 @@ int rtx_deinterleave_async(rtx_ctx *ctx, const void *d_gathered, uint32_t world,
 int rtx_resize_u8_to_async(rtx_ctx *ctx, void *image_u8, void *stream);
 int rtx_store_tiles_async(rtx_ctx *ctx, void *image_f32, void *stream);
 int rtx_adopt_u8(rtx_ctx *ctx, const void *d_image_u8);
+/* rtx_render + rtx_store_tiles_async as one blocking call: rtx_render_download for a tile partition whose host image is
+ * shared by the rank processes.  tile_world <= 1: same as rtx_render_download (bands traced and copied on two streams). */
+int rtx_render_store(rtx_ctx *ctx, void *image_f32);
 
 /* Device memory that other rank processes can map (CUDA IPC; 64-byte handle, any transport). */
 int rtx_peer_alloc(rtx_ctx *ctx, size_t bytes, void **device_ptr, unsigned char handle[64]);

@@ -100,6 +100,7 @@ struct rtx_ctx {
 	float *ext_image = nullptr;  /* caller-owned output (rtx_bind_output) */
 	bool ext_rowmajor = false;   /* ... and it is the whole row-major image although tile_world > 1 (rtx_bind_output_image) */
 	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums, d_lists, d_slists, d_raytab;
+	DevBuf d_tile_done;          /* rtx_render_store: units finished per local tile (fused store of the packet kernels) */
 	DevBuf d_hit_st, d_ao_ring;  /* ambient occlusion: (s, t) of the primary hits; sample table of the uniform method */
 	bool ao = false;
 	float ao_max_distance = 0.f; /* after the compiler_options.h round trip */
@@ -337,10 +338,10 @@ cudaError_t launch_pt(rtx_ctx *c, const RayWork &rw, const Work &pw, cudaStream_
 	return cudaGetLastError();
 }
 
-template <int BLOCK, int MINB, int SST, bool COUNT, bool RECORD, int RX, int RY, int MODE>
+template <int BLOCK, int MINB, int SST, bool COUNT, bool RECORD, int RX, int RY, int MODE, bool STORE = false>
 cudaError_t launch_packet_t(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
-	auto k = k_render_packet<BLOCK, MINB, SST, COUNT, RECORD, RX, RY, MODE>;
+	auto k = k_render_packet<BLOCK, MINB, SST, COUNT, RECORD, RX, RY, MODE, STORE>;
 	const size_t smem = (size_t)SST * BLOCK * sizeof(uint2) + (MODE == 1 ? (size_t)(BLOCK / 32) * (2 * RTX_CCAP) * 4 : 0);
 	int occ = 0;
 	cudaError_t e = resident_blocks(k, BLOCK, smem, c->device, &occ);
@@ -350,23 +351,25 @@ cudaError_t launch_packet_t(rtx_ctx *c, const Work &w, cudaStream_t st)
 	return cudaGetLastError();
 }
 
-template <bool COUNT, bool RECORD>
+/* STORE: the fused tile store of rtx_render_store (default tunables, no counters, no hit records) */
+template <bool COUNT, bool RECORD, bool STORE = false>
 cudaError_t launch_packet(rtx_ctx *c, const Work &w, cudaStream_t st)
 {
-	if (c->rays_per_thread == 2 && !w.frustum) return launch_packet_t<256, 3, 8, COUNT, RECORD, 2, 1, 0>(c, w, st);
+	if (c->rays_per_thread == 2 && !w.frustum) return launch_packet_t<256, 3, 8, COUNT, RECORD, 2, 1, 0, STORE>(c, w, st);
 	if (w.frustum) {
 		/* listed tiles first (no traversal code in that kernel), then the overflowed ones; both pull
 		 * units from the same kind of counter, so it is re-zeroed in between */
-		cudaError_t e = c->list_rays_per_thread == 1 ? launch_packet_t<256, 5, 0, COUNT, RECORD, 1, 1, 1>(c, w, st)
+		cudaError_t e = STORE ? launch_packet_t<256, 4, 0, COUNT, RECORD, 2, 1, 1, STORE>(c, w, st)
+		              : c->list_rays_per_thread == 1 ? launch_packet_t<256, 5, 0, COUNT, RECORD, 1, 1, 1>(c, w, st)
 		              : c->list_rays_per_thread == 2 ? launch_packet_t<256, 4, 0, COUNT, RECORD, 2, 1, 1>(c, w, st)
 		                                             : launch_packet_t<256, 3, 0, COUNT, RECORD, 2, 2, 1>(c, w, st);
 		if (e != cudaSuccess) return e;
 		e = cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st);
 		if (e != cudaSuccess) return e;
 		if ((e = phase_mark(c, st, RTX_PHASE_OVERFLOW)) != cudaSuccess) return e;
-		return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 2>(c, w, st);
+		return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 2, STORE>(c, w, st);
 	}
-	return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 0>(c, w, st);
+	return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 0, STORE>(c, w, st);
 }
 
 template <bool TOP, bool COUNT, bool RECORD>
@@ -393,6 +396,7 @@ cudaError_t launch_render(rtx_ctx *c, const Work &w, cudaStream_t st)
 		return rec ? launch_pt<false, true, 1>(c, none, w, st) : launch_pt<false, false, 1>(c, none, w, st);
 	}
 	if ((w.frustum || c->rays_per_thread > 1) && !top) {
+		if (w.store_image) return launch_packet<false, false, true>(c, w, st);        /* rtx_render_store checked cnt / rec */
 		if (cnt) return rec ? launch_packet<true, true>(c, w, st) : launch_packet<true, false>(c, w, st);
 		return rec ? launch_packet<false, true>(c, w, st) : launch_packet<false, false>(c, w, st);
 	}
@@ -621,7 +625,7 @@ void rtx_destroy(rtx_ctx *c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	DevBuf *bufs[] = { &c->t_parent, &c->t_build, &c->d_triangles, &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
 	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists, &c->d_slists, &c->d_raytab,
-	                   &c->d_hit_st, &c->d_ao_ring };
+	                   &c->d_hit_st, &c->d_ao_ring, &c->d_tile_done };
 	for (DevBuf *b : bufs) b->release();
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1040,7 +1044,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 	w.cam.jitter_seed = c->opt.jitter_seed;
 	w.cam.shading = c->opt.enable_shading ? 1 : 0;
 	w.cam.ux = w.cam.vy = nullptr;
-	const bool banded = host_dst && !c->ao && c->local_tiles > 0 && (size_t)c->W * c->H * sizeof(float) >= (16u << 20);
+	const bool banded = host_dst != nullptr && c->world == 1;
 	const int timing_was = c->phase_timing;
 	if (banded) c->phase_timing = 0;                   /* several passes per frame: the marks would be re-recorded */
 	CU(c, phase_mark(c, st, RTX_PHASE_TABLES));
@@ -1106,12 +1110,35 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 	const size_t frame_bytes = (size_t)c->W * c->H * sizeof(float);
 	uint32_t nbands = 1, passes = 1;
 	if (host_dst && !c->ao && c->local_tiles > 0) {
-		nbands = (uint32_t)(frame_bytes / (8u << 20));             /* >= 8 MB per copy keeps PCIe near its rate */
+		nbands = (uint32_t)(frame_bytes / c->world / (8u << 20));  /* >= 8 MB per copy keeps PCIe near its rate */
 		if (nbands > RTX_MAX_BANDS) nbands = RTX_MAX_BANDS;
 		if (nbands > c->tiles_y) nbands = c->tiles_y;
 		if (nbands < 1) nbands = 1;
 	}
-	if (host_dst && nbands > 1) {
+	if (host_dst && c->world > 1) {
+		/* rtx_render_store on a tile partition: trace, then store this rank's tiles into the whole image at host_dst
+		 * (mapped host or peer memory).  Measured: running the store kernel for finished bands next to the tracing of
+		 * the following ones is SLOWER (2 GPUs, C3: 10.0 ms against 7.7 ms) -- the persistent traversal CTAs own every
+		 * SM, so the store CTAs only ever run between bands, in pieces too small to fill the PCIe link. */
+		/* The packet kernels (frustum path) do the store themselves: the warp that finishes a tile's last unit sends the
+		 * tile, so the transfer runs inside the traversal kernel.  The other kernels are followed by k_store_tiles. */
+		const bool packet_kernel = persistent && c->top_smem == 0 && (w.frustum || c->rays_per_thread > 1) && !w.rowmajor &&
+		                           !c->counters && !rec && (!w.frustum || c->list_rays_per_thread == 2);
+		if (packet_kernel && c->local_tiles > 0) {
+			CU(c, c->d_tile_done.alloc((size_t)c->local_tiles * sizeof(unsigned int)));
+			CU(c, cudaMemsetAsync(c->d_tile_done.p, 0, (size_t)c->local_tiles * sizeof(unsigned int), st));
+			w.store_image = host_dst;
+			w.tile_done = c->d_tile_done.as<unsigned int>();
+		}
+		CU(c, phase_mark(c, st, RTX_PHASE_TRAVERSAL));
+		CU(c, launch_render(c, w, st));
+		if (!w.store_image && c->local_tiles > 0) {
+			k_store_tiles<<<c->local_tiles, 256, 0, st>>>(w.image, 0u, c->local_tiles, c->rank, c->world, c->tiles_x, c->W, c->H, host_dst);
+			CU(c, cudaGetLastError());
+		}
+		w.store_image = nullptr;
+		host_dst = nullptr;                                            /* nothing left to copy at the end of the frame */
+	} else if (host_dst && nbands > 1) {
 		if (!c->copy_stream) CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 		if (!c->copy_done) CU(c, cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
 		for (uint32_t b = 0; b < nbands; ++b)
@@ -1213,6 +1240,20 @@ int rtx_render_download(rtx_ctx *c, float *image)
 	if (!c || !image) return fail(c, RTX_ERR_ARG, "null argument");
 	if (c->world > 1) return fail(c, RTX_ERR_STATE, "this rank holds a tile partition; gather and de-interleave first");
 	const int rc = enqueue_render(c, c->stream, image);
+	if (rc != RTX_OK) return rc;
+	CU(c, cudaStreamSynchronize(c->stream));
+	return finish_stats(c);
+}
+
+/* Tile partition (tile_world > 1): trace this context's share and store it into the WHOLE row-major float image at
+ * `image_f32` -- page-locked host memory mapped into the device (rtx_host_register; every rank over its own PCIe link)
+ * or a peer's device memory.  tile_world <= 1: rtx_render_download.  Blocking.  Float image only. */
+int rtx_render_store(rtx_ctx *c, void *image_f32)
+{
+	if (!c || !image_f32) return fail(c, RTX_ERR_ARG, "null argument");
+	if (c->ao || c->record_hits) return fail(c, RTX_ERR_UNSUPPORTED, "rtx_render_store carries the float image only");
+	if (c->world > 1 && c->ext_image && c->ext_rowmajor) return fail(c, RTX_ERR_STATE, "unbind rtx_bind_output_image first");
+	const int rc = enqueue_render(c, c->stream, static_cast<float *>(image_f32));
 	if (rc != RTX_OK) return rc;
 	CU(c, cudaStreamSynchronize(c->stream));
 	return finish_stats(c);
@@ -1407,7 +1448,7 @@ int rtx_store_tiles_async(rtx_ctx *c, void *image_f32, void *stream)
 		return RTX_OK;
 	}
 	if (c->local_tiles == 0) return RTX_OK;
-	k_store_tiles<<<c->local_tiles, 256, 0, st>>>(src, c->local_tiles, c->rank, c->world, c->tiles_x, c->W, c->H, static_cast<float *>(image_f32));
+	k_store_tiles<<<c->local_tiles, 256, 0, st>>>(src, 0u, c->local_tiles, c->rank, c->world, c->tiles_x, c->W, c->H, static_cast<float *>(image_f32));
 	CU(c, cudaGetLastError());
 	return RTX_OK;
 }

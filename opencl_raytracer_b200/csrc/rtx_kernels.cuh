@@ -297,6 +297,10 @@ struct Work {
 	uint32_t num_units;          /* tile_count * 32 */
 	unsigned int *counter;       /* persistent-kernel work counter (zeroed before launch) */
 	float *image;                /* world == 1: row-major W x H; else compact [local_tile][32][32] */
+	float *store_image;          /* world > 1, packet kernels: the whole row-major image in mapped host / peer memory; the warp that
+	                                finishes a tile's last unit copies the tile there (128-byte rows), so the transfer runs while
+	                                the other tiles are still being traced (rtx_render_store) */
+	unsigned int *tile_done;     /* ... units finished per local tile (zeroed before the frame) */
 	int rowmajor;                /* world > 1: `image` is the whole row-major W x H image (a peer's or mapped host memory,
 	                                rtx_bind_output_image) and this rank writes only the pixels of its own tiles */
 	uint32_t *face_id;           /* optional (record mode), same indexing as image */
@@ -759,7 +763,8 @@ RTX_DEV void intersect_candidates(const SceneDev &sc, const uint32_t *__restrict
 /* MODE 0: per-ray/packet traversal for every tile.
  * MODE 1: candidate lists only (tiles whose list overflowed are skipped) -- no traversal code in the kernel.
  * MODE 2: traversal for the tiles MODE 1 skipped; exits at once when k_frustum_collect saw no overflow. */
-template <int BLOCK, int MIN_BLOCKS, int SMEM_STACK, bool COUNT, bool RECORD, int RX, int RY, int MODE>
+/* STORE: the fused tile store of rtx_render_store (a separate instantiation: the plain kernel keeps its registers). */
+template <int BLOCK, int MIN_BLOCKS, int SMEM_STACK, bool COUNT, bool RECORD, int RX, int RY, int MODE, bool STORE = false>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
 k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 {
@@ -853,6 +858,33 @@ k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 			}
 		}
 		__syncwarp();
+		if (STORE) {
+			/* fused store: whoever finishes the tile's last unit sends the whole tile (compact, 4 KB, still in L2) to its
+			 * place in the caller's image -- full 128-byte rows, posted writes, while the other warps keep tracing */
+			unsigned int done = 0;
+			if (lane == 0) { __threadfence(); done = atomicAdd(w.tile_done + ltile, 1u); }
+			done = __shfl_sync(0xffffffffu, done, 0);
+			if (done == UPT - 1u) {
+				__threadfence();
+				const float *src = w.image + (size_t)ltile * (RTX_TILE * RTX_TILE);
+				const uint32_t x0 = tx * RTX_TILE, y0 = ty * RTX_TILE;
+				if ((w.cam.W & 3u) == 0 && (reinterpret_cast<uintptr_t>(w.store_image) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w.image) & 15u) == 0) {
+#pragma unroll 2
+					for (uint32_t i = lane; i < RTX_TILE * RTX_TILE / 4; i += 32) {
+						const uint32_t py = i >> 3, px = (i & 7u) << 2;
+						if (y0 + py < w.cam.H && x0 + px < w.cam.W)
+							__stcs(reinterpret_cast<float4 *>(w.store_image + (size_t)(y0 + py) * w.cam.W + x0 + px),
+							       __ldcg(reinterpret_cast<const float4 *>(src + py * RTX_TILE + px)));
+					}
+				} else {
+					for (uint32_t i = lane; i < RTX_TILE * RTX_TILE; i += 32) {
+						const uint32_t px = i & 31u, py = i >> 5;
+						if (x0 + px < w.cam.W && y0 + py < w.cam.H) w.store_image[(size_t)(y0 + py) * w.cam.W + x0 + px] = __ldcg(src + i);
+					}
+				}
+			}
+			__syncwarp();
+		}
 	}
 }
 
@@ -1534,10 +1566,10 @@ __global__ void k_resize_tiles_u8_to(const float *__restrict__ tiles, uint32_t l
  * the device (rtx_host_register: every rank's tiles leave over its own PCIe link).  One CTA per tile, 128-bit stores
  * (a tile row = 128 contiguous bytes). */
 __global__ void __launch_bounds__(256)
-k_store_tiles(const float *__restrict__ tiles, uint32_t local_tiles, uint32_t rank, uint32_t world, uint32_t tiles_x,
+k_store_tiles(const float *__restrict__ tiles, uint32_t tile_begin, uint32_t local_tiles, uint32_t rank, uint32_t world, uint32_t tiles_x,
               uint32_t W, uint32_t H, float *__restrict__ image)
 {
-	const uint32_t lt = blockIdx.x;
+	const uint32_t lt = tile_begin + blockIdx.x;           /* local tiles [tile_begin, local_tiles) */
 	if (lt >= local_tiles) return;
 	const uint32_t tile = lt * world + rank, tx = tile % tiles_x, ty = tile / tiles_x;
 	const float *src = tiles + (size_t)lt * (RTX_TILE * RTX_TILE);

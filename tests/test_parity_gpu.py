@@ -501,6 +501,15 @@ def test_direct_stores_equal_single_image(po, soup_scene, world, w, h_, ss):
                 c.store_tiles_async(d_f32)           # no compact tile buffer exists in this mode
             c.bind_output_image(0)
         assert np.array_equal(shared, single)
+        shared[:] = -1.0
+        for c in ctxs:                                   # ... and render + store as one call (store kernel after the traversal)
+            c.render_store(alias)
+        assert np.array_equal(shared, single)
+        shared[:] = -1.0
+        for c in ctxs:                                   # ... with the frustum path: the packet kernel stores finished tiles itself
+            c.set_tunable(host.TUNE_FRUSTUM, 1)
+            c.render_store(alias)
+        assert np.array_equal(shared, single)
         host.host_unregister(shared)
         ctxs[0].peer_free(d_u8)
         ctxs[0].peer_free(d_f32)
