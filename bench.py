@@ -57,12 +57,16 @@ CPU_ROW_STEP = 16      # both CPU legs time every 16th row of the frame (rows 8,
 def make_config(desc, scene_name, ntris, tw, th, world, gather):
     """The `config` object, identical in the GPU arm and in --impl reference (the driver compares the two)."""
     nrows = len(range(CPU_ROW_STEP // 2, th, CPU_ROW_STEP))
+    how = {"auto": "every rank's resize kernel stores its bytes into rank 0's image over NVLink peer memory, ordered by a one-element "
+                   "all-reduce (one NCCL gather of the bytes + de-interleave where the GPUs cannot map each other's memory)",
+           "p2p_u8": "every rank's resize kernel stores its bytes into rank 0's image over NVLink peer memory, ordered by a one-element all-reduce",
+           "p2p_float": "every rank's traversal kernel sends finished float tiles into rank 0's image over NVLink peer memory, ordered by a "
+                        "one-element all-reduce",
+           "u8": "1 NCCL gather of the bytes + de-interleave", "float": "1 NCCL gather of the float tiles + de-interleave"}[gather]
     return {"workload": desc, "scene": scene_name, "triangles": int(ntris), "rays_per_step": int(tw * th),
-            "parallelism": "interleaved 32x32 tiles over %d GPU(s), scene replicated, 1 NCCL gather/frame" % world,
-            "step": "trace + RayTracer::resize on the device%s -> %s image on rank 0" % (
-                "" if world == 1 else (" + 1 NCCL gather + de-interleave" if not gather.startswith("p2p_") else
-                                       ", every rank's kernel storing its share into rank 0's image over NVLink peer memory + 1-element all-reduce"),
-                "byte" if gather.endswith("u8") else "float"),
+            "parallelism": "interleaved 32x32 tiles over %d GPU(s), scene replicated, frame assembled on rank 0" % world,
+            "step": "trace + RayTracer::resize on the device -> %s image on rank 0%s" % (
+                "float" if gather.endswith("float") else "byte", "" if world == 1 else " (N > 1: " + how + ")"),
             "l2": "flushed between timed iterations (256 MiB memset, untimed)",
             "reference_arm_sample": "the CPU arm (--impl reference, cpu_baseline) times every %d-th row of the same %dx%d frame "
                                     "(%d rows = %.2f M rays per pass) on all host cores" % (CPU_ROW_STEP, tw, th, nrows, nrows * tw / 1e6)}
@@ -455,11 +459,11 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="u8", choices=["u8", "float", "p2p_u8", "p2p_float"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "u8", "float", "p2p_u8", "p2p_float"],
                     help="what a step ends with on rank 0 and how it gets there (N > 1): u8 = the byte image after RayTracer::resize on "
                          "the device, every rank resizes its own tiles and ONE NCCL gather moves bytes (default); float = ONE NCCL gather "
                          "of the float tiles; p2p_* = no collective, every rank's kernel stores its share into rank 0's image over NVLink "
-                         "peer memory (multigpu.TiledRenderer)")
+                         "peer memory (multigpu.TiledRenderer); auto (default) = p2p_u8 when the GPUs can map each other's memory, else u8")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -528,7 +532,17 @@ def main():
     # ---------------- value: scene resident, device-timed ----------------
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)                       # kernels, NCCL gather and the events all use this stream
-    r = multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather=args.gather)
+    requested_gather, r = args.gather, None
+    if args.gather == "auto":
+        args.gather = "u8"
+        if world > 1:
+            try:
+                r = multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather="p2p_u8")
+                args.gather = "p2p_u8"
+            except RuntimeError:                          # raised on every rank together (multigpu.TiledRenderer)
+                r = None
+    if r is None:
+        r = multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather=args.gather)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     for _ in range(args.warmup):
         r.render_frame()
@@ -659,7 +673,7 @@ def main():
         out_b = torch.empty((height, width), dtype=torch.uint8).pin_memory().numpy() if rank == 0 else None
         # N > 1: download(float*) needs the float tiles gathered, download_u8 the byte tiles -- one renderer per payload
         r_float = r if (world == 1 or args.gather == "float") else multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather="float")
-        r_u8 = r if (world == 1 or args.gather == "u8") else multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather="u8")
+        r_u8 = r if (world == 1 or args.gather.endswith("u8")) else multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather="u8")
         hr = r.host
 
         phase = {}
@@ -876,7 +890,8 @@ def main():
             "metric": METRIC.get(args.workload, METRIC["c3"]), "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": make_config(desc, sc.name, sc.num_triangles, tw, th, world, args.gather),
+            "config": make_config(desc, sc.name, sc.num_triangles, tw, th, world, requested_gather),
+            "gather": args.gather,
             "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(lt.item()),
             "roofline": roofline, "cpu_baseline": cpu, "parity_check": parity, "phases_ms": phases_ms, "other_gather": other, "extras": extras,
             "step_ms": [float(x) for x in step_ms],

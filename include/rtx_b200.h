@@ -259,6 +259,7 @@ int rtx_adopt_u8(rtx_ctx *ctx, const void *d_image_u8);
 /* rtx_render + rtx_store_tiles_async as one blocking call: rtx_render_download for a tile partition whose host image is
  * shared by the rank processes.  tile_world <= 1: same as rtx_render_download (bands traced and copied on two streams). */
 int rtx_render_store(rtx_ctx *ctx, void *image_f32);
+int rtx_render_store_async(rtx_ctx *ctx, void *image_f32, void *stream);    /* tile partitions only; enqueues and returns */
 
 /* Device memory that other rank processes can map (CUDA IPC; 64-byte handle, any transport). */
 int rtx_peer_alloc(rtx_ctx *ctx, size_t bytes, void **device_ptr, unsigned char handle[64]);

@@ -100,6 +100,7 @@ struct rtx_ctx {
 	float *ext_image = nullptr;  /* caller-owned output (rtx_bind_output) */
 	bool ext_rowmajor = false;   /* ... and it is the whole row-major image although tile_world > 1 (rtx_bind_output_image) */
 	DevBuf d_image, d_image_full, d_face_id, d_dist, d_u8, d_counter, d_counters, d_sums, d_lists, d_slists, d_raytab;
+	cudaEvent_t raytab_ev = nullptr;   /* set once the ray tables are filled (enqueue_render) */
 	DevBuf d_tile_done;          /* rtx_render_store: units finished per local tile (fused store of the packet kernels) */
 	DevBuf d_hit_st, d_ao_ring;  /* ambient occlusion: (s, t) of the primary hits; sample table of the uniform method */
 	bool ao = false;
@@ -364,10 +365,10 @@ cudaError_t launch_packet(rtx_ctx *c, const Work &w, cudaStream_t st)
 		              : c->list_rays_per_thread == 2 ? launch_packet_t<256, 4, 0, COUNT, RECORD, 2, 1, 1>(c, w, st)
 		                                             : launch_packet_t<256, 3, 0, COUNT, RECORD, 2, 2, 1>(c, w, st);
 		if (e != cudaSuccess) return e;
-		e = cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st);
-		if (e != cudaSuccess) return e;
 		if ((e = phase_mark(c, st, RTX_PHASE_OVERFLOW)) != cudaSuccess) return e;
-		return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 2, STORE>(c, w, st);
+		Work w2 = w;
+		w2.counter = w.counter + 1;            /* its own work counter, zeroed together with the first at the start of the frame / band */
+		return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 2, STORE>(c, w2, st);
 	}
 	return launch_packet_t<256, 2, 8, COUNT, RECORD, 2, 2, 0, STORE>(c, w, st);
 }
@@ -631,6 +632,7 @@ void rtx_destroy(rtx_ctx *c)
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	for (cudaEvent_t e : c->band_ev) if (e) cudaEventDestroy(e);
 	for (cudaEvent_t e : c->ph_ev) if (e) cudaEventDestroy(e);
+	if (c->raytab_ev) cudaEventDestroy(c->raytab_ev);
 	for (int k = 0; k < 2; ++k) {
 		c->r_o[k].release(); c->r_d[k].release(); c->r_f[k].release(); c->r_t[k].release();
 		if (c->r_ev_in[k]) cudaEventDestroy(c->r_ev_in[k]);
@@ -790,7 +792,7 @@ static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nver
 			CUU(cudaGetLastError());
 			CUU(cudaStreamSynchronize(st));
 		} else {
-			unsigned int *fat = c->d_counter.as<unsigned int>() + 2;
+			unsigned int *fat = c->d_counter.as<unsigned int>() + 3;
 			CUU(cudaMemsetAsync(fat, 0, sizeof(unsigned int), st));
 			k_slack_leaves<<<grid, 256, 0, st>>>(c->d_pairs.as<float4>(), c->d_tris.as<float4>(), (uint32_t)num_pairs, (uint32_t)pair_stride, nullptr, fat);
 			CUU(cudaGetLastError());
@@ -1048,16 +1050,27 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 	const int timing_was = c->phase_timing;
 	if (banded) c->phase_timing = 0;                   /* several passes per frame: the marks would be re-recorded */
 	CU(c, phase_mark(c, st, RTX_PHASE_TABLES));
+	uint32_t table_launch = 0;
 	if (c->ray_tables && c->opt.jitter_seed == 0) {
-		CU(c, c->d_raytab.alloc(((size_t)c->W + c->H) * sizeof(float)));
-		float *ux = c->d_raytab.as<float>(), *vy = ux + c->W;
-		const uint32_t m = c->W > c->H ? c->W : c->H;
-		k_ray_tables<<<(m + 255) / 256, 256, 0, st>>>(w.cam, ux, vy);
-		CU(c, cudaGetLastError());
+		/* the tables depend on the camera only, which is fixed for the context: filled by the first frame, then reused
+		 * (later frames on another stream wait for the event of that first launch) */
+		float *ux = c->d_raytab.as<float>(), *vy = ux ? ux + c->W : nullptr;
+		if (!c->raytab_ev) {
+			CU(c, c->d_raytab.alloc(((size_t)c->W + c->H) * sizeof(float)));
+			ux = c->d_raytab.as<float>();
+			vy = ux + c->W;
+			const uint32_t m = c->W > c->H ? c->W : c->H;
+			k_ray_tables<<<(m + 255) / 256, 256, 0, st>>>(w.cam, ux, vy);
+			CU(c, cudaGetLastError());
+			CU(c, cudaEventCreateWithFlags(&c->raytab_ev, cudaEventDisableTiming));
+			CU(c, cudaEventRecord(c->raytab_ev, st));
+			table_launch = 1;
+		} else {
+			CU(c, cudaStreamWaitEvent(st, c->raytab_ev, 0));
+		}
 		w.cam.ux = ux;
 		w.cam.vy = vy;
 	}
-	const uint32_t table_launch = w.cam.ux ? 1u : 0u;
 	w.tiles_x = c->tiles_x;
 	w.tiles_y = c->tiles_y;
 	w.rank = c->rank;
@@ -1084,7 +1097,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 		CU(c, c->d_lists.alloc((size_t)c->local_tiles * RTX_LIST_STRIDE * 4));
 		CU(c, c->d_slists.alloc((size_t)((c->tiles_x + RTX_SUPER - 1) / RTX_SUPER) * ((c->tiles_y + RTX_SUPER - 1) / RTX_SUPER) * RTX_SLIST_STRIDE * 4));
 		w.lists = c->d_lists.as<uint32_t>();
-		w.overflow_tiles = c->d_counter.as<unsigned int>() + 1;
+		w.overflow_tiles = c->d_counter.as<unsigned int>() + 2;      /* words: [0] work counter, [1] work counter of the overflow launch, [2] overflowed tiles, [3] upload scratch */
 	}
 	CU(c, cudaMemsetAsync(c->d_counter.p, 0, 4 * sizeof(unsigned int), st));
 	if (c->counters) CU(c, cudaMemsetAsync(c->d_counters.p, 0, sizeof(Counters), st));
@@ -1156,7 +1169,7 @@ static int enqueue_render(rtx_ctx *c, cudaStream_t st, float *host_dst = nullptr
 			w.tile_begin = r0 * c->tiles_x;
 			w.tile_count = (r1 - r0) * c->tiles_x;
 			w.num_units = w.tile_count * 32u;
-			if (b > 0) CU(c, cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st));   /* the work counter only */
+			if (b > 0) CU(c, cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned int), st));   /* the two work counters only */
 			CU(c, launch_render(c, w, st));
 			CU(c, cudaEventRecord(c->band_ev[b], st));
 			CU(c, cudaStreamWaitEvent(c->copy_stream, c->band_ev[b], 0));
@@ -1248,6 +1261,15 @@ int rtx_render_download(rtx_ctx *c, float *image)
 /* Tile partition (tile_world > 1): trace this context's share and store it into the WHOLE row-major float image at
  * `image_f32` -- page-locked host memory mapped into the device (rtx_host_register; every rank over its own PCIe link)
  * or a peer's device memory.  tile_world <= 1: rtx_render_download.  Blocking.  Float image only. */
+int rtx_render_store_async(rtx_ctx *c, void *image_f32, void *stream)
+{
+	if (!c || !image_f32) return fail(c, RTX_ERR_ARG, "null argument");
+	if (c->ao || c->record_hits) return fail(c, RTX_ERR_UNSUPPORTED, "rtx_render_store carries the float image only");
+	if (c->world > 1 && c->ext_image && c->ext_rowmajor) return fail(c, RTX_ERR_STATE, "unbind rtx_bind_output_image first");
+	if (c->world <= 1) return fail(c, RTX_ERR_STATE, "rtx_render_store_async is for tile partitions; use rtx_render_download / rtx_render_async");
+	return enqueue_render(c, static_cast<cudaStream_t>(stream), static_cast<float *>(image_f32));
+}
+
 int rtx_render_store(rtx_ctx *c, void *image_f32)
 {
 	if (!c || !image_f32) return fail(c, RTX_ERR_ARG, "null argument");

@@ -39,7 +39,7 @@ ABI_SYMBOLS = (
     "rtx_probe_bandwidth", "rtx_resize_u8_async", "rtx_deinterleave_u8_async", "rtx_render_download",
     "rtx_upload_mesh", "rtx_download_tree", "rtx_build_stats", "rtx_download_normals",
     "rtx_resize_u8_to_async", "rtx_store_tiles_async", "rtx_adopt_u8", "rtx_peer_alloc", "rtx_peer_open", "rtx_peer_close",
-    "rtx_peer_free", "rtx_host_register", "rtx_host_unregister", "rtx_phase_ms", "rtx_copy_to_host", "rtx_bind_output_image", "rtx_render_store",
+    "rtx_peer_free", "rtx_host_register", "rtx_host_unregister", "rtx_phase_ms", "rtx_copy_to_host", "rtx_bind_output_image", "rtx_render_store", "rtx_render_store_async",
 )
 
 
@@ -175,6 +175,8 @@ def load_library():
     lib.rtx_bind_output_image.argtypes = [vp, vp]
     lib.rtx_render_store.restype = C.c_int
     lib.rtx_render_store.argtypes = [vp, vp]
+    lib.rtx_render_store_async.restype = C.c_int
+    lib.rtx_render_store_async.argtypes = [vp, vp, vp]
     lib.rtx_copy_to_host.restype = C.c_int
     lib.rtx_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
     lib.rtx_phase_ms.restype = C.c_int
@@ -459,6 +461,9 @@ class CudaHost:
     def render_store(self, image_f32: int):
         """``__call__`` + ``store_tiles_async`` in one blocking call, band by band (the stores overlap the tracing)."""
         self._ck(self._lib.rtx_render_store(self._ctx, C.c_void_p(image_f32)))
+
+    def render_store_async(self, image_f32: int, stream: int = 0):
+        self._ck(self._lib.rtx_render_store_async(self._ctx, C.c_void_p(image_f32), C.c_void_p(stream)))
 
     def adopt_u8(self, d_image_u8: int):
         self._ck(self._lib.rtx_adopt_u8(self._ctx, C.c_void_p(d_image_u8)))

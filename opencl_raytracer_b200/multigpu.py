@@ -94,8 +94,10 @@ class TiledRenderer:
                    final image through NVLink peer memory (CUDA IPC mapping, set up once); the frame ends with a
                    one-element all-reduce on the same stream, which completes on rank 0 only when every rank's store
                    kernel has finished.  Two images alternate, so rank 0 may read frame k while frame k+1 is written.
-      "p2p_float"  the float image: every rank's traversal kernel writes its pixels straight into rank 0's row-major
-                   image (rtx_bind_output_image on the peer mapping), so the transfer overlaps the tracing; same rendezvous
+      "p2p_float"  the float image: in every rank's traversal kernel the warp that finishes a tile sends it to its place in
+                   rank 0's row-major image (rtx_render_store_async on the peer mapping), so the transfer overlaps the
+                   tracing; same rendezvous.  (Writing each pixel remotely as it is shaded, rtx_bind_output_image, moves
+                   8-byte pieces over NVLink: 1.68 ms against 1.03 ms of tracing at 4 GPUs.)
     """
 
     def __init__(self, rt, scene, rank: int, world: int, device: int, jitter_seed: int = 0, gather: str = "float"):
@@ -165,9 +167,11 @@ class TiledRenderer:
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         if self.timing:
             self._ev = []
-        if self.gather == "p2p_float":       # the pixels go straight into rank 0's image as they are shaded
-            self.host.bind_output_image(self.peer[self.frame & 1])
-        self.host.render_async(stream)
+        if self.gather == "p2p_float":
+            # the traversal kernel sends every finished tile to its place in rank 0's image (128-byte rows over NVLink)
+            self.host.render_store_async(self.peer[self.frame & 1], stream)
+        else:
+            self.host.render_async(stream)
         self.kernel_launches += self.host.last_launches()
         self._mark("resize")
         if self.gather == "u8":
