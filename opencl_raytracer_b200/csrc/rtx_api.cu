@@ -1396,7 +1396,8 @@ int rtx_deinterleave_u8_async(rtx_ctx *c, const void *d_gathered, uint32_t world
 	CU(c, c->d_u8.alloc((size_t)c->opt.width * c->opt.height));
 	uint32_t tx, ty, tpr;
 	rtx_tile_layout(c->W, c->H, world, &tx, &ty, &tpr);
-	k_deinterleave_u8<<<tx * ty, 64, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned char *>(d_gathered), world, tpr, tx, ty, n,
+	const size_t rows = (size_t)tx * ty * (RTX_TILE / n);
+	k_deinterleave_u8<<<(unsigned)((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned char *>(d_gathered), world, tpr, tx, ty, n,
 	                                                                          c->opt.width, c->opt.height, c->d_u8.as<unsigned char>());
 	CU(c, cudaGetLastError());
 	c->u8_valid = true;

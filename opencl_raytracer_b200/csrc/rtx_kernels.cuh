@@ -1588,20 +1588,27 @@ k_store_tiles(const float *__restrict__ tiles, uint32_t tile_begin, uint32_t loc
 	}
 }
 
-/* rank-major gathered compact u8 tiles -> row-major width x height byte image (rank 0) */
+/* rank-major gathered compact u8 tiles -> row-major width x height byte image (rank 0).  One thread per output row of
+ * a tile (m = 32 / n bytes; one 64-bit load + store when m == 8 and everything is aligned). */
 __global__ void k_deinterleave_u8(const unsigned char *__restrict__ gathered, uint32_t world, uint32_t tiles_per_rank,
                                   uint32_t tiles_x, uint32_t tiles_y, uint32_t n, uint32_t width, uint32_t height,
                                   unsigned char *__restrict__ image)
 {
-	const uint32_t tile = blockIdx.x;
-	if (tile >= tiles_x * tiles_y) return;
 	const uint32_t m = RTX_TILE / n;
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (size_t)tiles_x * tiles_y * m) return;
+	const uint32_t tile = (uint32_t)(i / m), oy = (uint32_t)(i % m);
 	const uint32_t rank = tile % world, ltile = tile / world;
-	const unsigned char *src = gathered + ((size_t)rank * tiles_per_rank + ltile) * (m * m);
+	const unsigned char *src = gathered + ((size_t)rank * tiles_per_rank + ltile) * (m * m) + oy * m;
 	const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
-	for (uint32_t i = threadIdx.x; i < m * m; i += blockDim.x) {
-		const uint32_t x = tx * m + i % m, y = ty * m + i / m;
-		if (x < width && y < height) image[(size_t)y * width + x] = src[i];
+	const uint32_t x0 = tx * m, y = ty * m + oy;
+	if (y >= height) return;
+	unsigned char *dst = image + (size_t)y * width + x0;
+	if (m == 8 && x0 + 8 <= width && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 7u) == 0) {
+		*reinterpret_cast<uint2 *>(dst) = __ldcs(reinterpret_cast<const uint2 *>(src));
+	} else {
+		for (uint32_t k = 0; k < m; ++k)
+			if (x0 + k < width) dst[k] = src[k];
 	}
 }
 

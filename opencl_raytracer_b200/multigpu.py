@@ -90,10 +90,10 @@ class TiledRenderer:
       "float"      ONE NCCL gather of the float tiles + de-interleave kernel: the image ``download(float*)`` returns
       "u8"         every rank applies RayTracer::resize to its own tiles, ONE NCCL gather of the bytes + de-interleave
                    ((n*n*4)x less traffic into rank 0; needs sqrt(nSuperSamples) to divide 32)
-      "p2p_u8"     no collective on the data path: every rank's resize kernel stores its bytes straight into rank 0's
-                   final image through NVLink peer memory (CUDA IPC mapping, set up once); the frame ends with a
-                   one-element all-reduce on the same stream, which completes on rank 0 only when every rank's store
-                   kernel has finished.  Two images alternate, so rank 0 may read frame k while frame k+1 is written.
+      "p2p_u8"     no collective on the data path: every rank's resize kernel stores its bytes straight into its slot of
+                   a buffer in rank 0's memory through NVLink peer memory (CUDA IPC mapping, set up once); a one-element
+                   all-reduce on the same stream completes on rank 0 only when every rank's store kernel has finished;
+                   rank 0 de-interleaves.  Two buffers alternate, so rank 0 may read frame k while k+1 is written.
       "p2p_float"  the float image: in every rank's traversal kernel the warp that finishes a tile sends it to its place in
                    rank 0's row-major image (rtx_render_store_async on the peer mapping), so the transfer overlaps the
                    tracing; same rendezvous.  (Writing each pixel remotely as it is shaded, rtx_bind_output_image, moves
@@ -129,7 +129,9 @@ class TiledRenderer:
             self.local_u8 = torch.zeros(tile_counts(rt.totalWidth, rt.totalHeight, world)[2] * m * m, dtype=torch.uint8, device=self.dev)
         if gather.startswith("p2p_"):
             import torch.distributed as dist
-            nbytes = rt.options.width * rt.options.height if gather == "p2p_u8" else rt.totalWidth * rt.totalHeight * 4
+            m = TILE // rt.n if gather == "p2p_u8" else 0
+            self.u8_per_rank = tile_counts(rt.totalWidth, rt.totalHeight, world)[2] * m * m
+            nbytes = world * self.u8_per_rank if gather == "p2p_u8" else rt.totalWidth * rt.totalHeight * 4
             # collective set-up that cannot leave a rank waiting: every step ends with all ranks knowing whether it worked
             box, err = [None], None
             if rank == 0:
@@ -198,12 +200,17 @@ class TiledRenderer:
             import torch.distributed as dist
             target = self.peer[self.frame & 1]
             if self.gather == "p2p_u8":
-                self.host.resize_u8_to_async(target, stream)      # resize + store into rank 0's image, one kernel
+                # resize this rank's tiles and store the bytes, compact and contiguous, into this rank's slot of the buffer
+                # in rank 0's memory: one kernel, coalesced remote writes (storing every 8-byte tile row at its final
+                # row-major place instead cost 0.07 ms against 0.02 ms at 4 GPUs)
+                self.host.resize_u8_async(target + self.rank * self.u8_per_rank, self.u8_per_rank, stream)
                 self.kernel_launches += 1
             self._mark("gather")
             dist.all_reduce(self.flag)                            # rendezvous: every rank's stores have landed
             if self.rank == 0 and self.gather == "p2p_u8":
-                self.host.adopt_u8(target)
+                self._mark("deinterleave")
+                self.host.deinterleave_u8_async(target, self.world, stream)
+                self.kernel_launches += 1
             self.last_target = target
         self._mark("end")
         self.frame += 1
