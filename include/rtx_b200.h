@@ -282,6 +282,11 @@ int rtx_host_unregister(void *p);
 #define RTX_NUM_PHASES          6
 int rtx_phase_ms(const rtx_ctx *ctx, double *ms);
 
+/* Only in the bounds-checked debug build (lib/librtx_b200_dbg.so, -DRTX_DEBUG_BOUNDS): every device-side index into the
+ * scene arrays, stacks, queues and candidate lists is range-checked; out = { violations since the last call, source
+ * line, index, limit of the first one }.  The release build returns RTX_ERR_UNSUPPORTED. */
+int rtx_debug_bounds(rtx_ctx *ctx, unsigned int out[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -816,6 +816,7 @@ static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nver
 	c->sc.ref_nodes = c->d_ref_nodes.as<uint32_t>();
 	c->sc.ref_aabbs = c->d_ref_aabbs.as<float4>();
 	c->sc.num_pairs = (uint32_t)pair_stride;            /* distance between the octant copies */
+	c->sc.pair_count = (uint32_t)num_pairs;
 	c->sc.top_pairs = c->top_smem > 0 ? top_pairs : 0;
 	c->sc.num_tris = (uint32_t)ntris;
 	c->sc.verify_leafbox = c->leaf_size > 1 ? 1u : 0u;
@@ -1562,6 +1563,24 @@ int rtx_copy_to_host(rtx_ctx *c, void *host_dst, const void *device_src, size_t 
 	CU(c, cudaDeviceSynchronize());
 	CU(c, cudaMemcpy(host_dst, device_src, bytes, cudaMemcpyDeviceToHost));
 	return RTX_OK;
+}
+
+/* Debug build only (RTX_DEBUG_BOUNDS): out-of-range indices the kernels caught since the last call
+ * (count, then source line / index / limit of the first one); the counters are reset. */
+int rtx_debug_bounds(rtx_ctx *c, unsigned int out[4])
+{
+	if (!c || !out) return fail(c, RTX_ERR_ARG, "null argument");
+#ifdef RTX_DEBUG_BOUNDS
+	CU(c, cudaSetDevice(c->device));
+	CU(c, cudaDeviceSynchronize());
+	CU(c, cudaMemcpyFromSymbol(out, g_rtx_bounds, 4 * sizeof(unsigned int)));
+	const unsigned int zero[4] = { 0u, 0u, 0u, 0u };
+	CU(c, cudaMemcpyToSymbol(g_rtx_bounds, zero, sizeof zero));
+	return RTX_OK;
+#else
+	out[0] = out[1] = out[2] = out[3] = 0u;
+	return fail(c, RTX_ERR_UNSUPPORTED, "this library was built without RTX_DEBUG_BOUNDS (make -C opencl_raytracer_b200/csrc debug)");
+#endif
 }
 
 int rtx_phase_ms(const rtx_ctx *c, double *ms)

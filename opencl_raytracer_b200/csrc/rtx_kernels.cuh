@@ -29,7 +29,8 @@ struct SceneDev {
 	const float4 *tnormals;
 	const uint32_t *ref_nodes;
 	const float4 *ref_aabbs;
-	uint32_t num_pairs;
+	uint32_t num_pairs;       /* distance (in pairs) between the octant copies */
+	uint32_t pair_count;      /* pairs actually in the tree (<= num_pairs) */
 	uint32_t top_pairs;       /* pairs staged in shared memory */
 	uint32_t num_tris;
 	uint32_t verify_leafbox;  /* leaves hold > 1 triangle: per-triangle leaf box must be checked */
@@ -70,7 +71,7 @@ __device__ __noinline__ void walk_reference(const SceneDev &sc, f3 o, f3 d, floa
 			i += node_count;
 		} else {
 			if (node_count == 1) {
-				const float4 *q = sc.tris + 4 * (size_t)tri;
+				const float4 *q = sc.tris + 4 * RTX_IDX(tri, sc.num_tris);
 				TriHit h;
 				if (COUNT) ++tests;
 				if (triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, __int_as_float(0x7f800000), h)) {
@@ -194,7 +195,7 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ pai
 				const float4 *q = s_top + 4 * cur;
 				q0 = q[0]; q1 = q[1]; q2 = q[2]; q3 = q[3];
 			} else {
-				const float4 *q = pairs + 4 * (size_t)cur;
+				const float4 *q = pairs + 4 * RTX_IDX(cur, sc.pair_count);
 				q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2); q3 = __ldg(q + 3);
 			}
 			if (COUNT) visits += 2;
@@ -208,7 +209,7 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ pai
 			const bool r_first = hitR && (!hitL || R.tmin < L.tmin);
 			if (hitL && hitR) {
 				const uint2 e = make_uint2((uint32_t)(r_first ? refL : refR), __float_as_uint(r_first ? cL : cR));
-				if (SMEM_STACK > 0 && sp < SMEM_STACK) s_stack[sp * stride] = e; else l_stack[sp - SMEM_STACK] = e;
+				if (SMEM_STACK > 0 && sp < SMEM_STACK) s_stack[sp * stride] = e; else l_stack[RTX_IDX(sp - SMEM_STACK, RTX_STACK_MAX - SMEM_STACK)] = e;
 				++sp;
 			}
 			cur = r_first ? refR : refL;
@@ -219,13 +220,13 @@ RTX_DEV void traverse_ordered(const SceneDev &sc, const float4 *__restrict__ pai
 			const uint32_t first = enc >> 3, count = (enc & 7u) + 1u;
 			for (uint32_t k = 0; k < count; ++k) {
 				const uint32_t tri = first + k;
-				const float4 *q = sc.tris + 4 * (size_t)tri;
+				const float4 *q = sc.tris + 4 * RTX_IDX(tri, sc.num_tris);
 				TriHit h;
 				if (COUNT) ++tests;
 				if (!triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, cull, h)) continue;
 				if (!(h.dist < best.dist || (h.dist == best.dist && tri < best.tri))) continue;
 				if (sc.verify_leafbox) {
-					const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+					const float4 lo = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris)), hi = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris) + 1);
 					if (COUNT) ++lbtests;
 					if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), o, d, max_distance)) continue;
 				}
@@ -410,7 +411,7 @@ RTX_DEV void traverse_packet(const SceneDev &sc, const float4 *__restrict__ pair
 
 	for (;;) {
 		while (cur >= 0) {
-			const float4 *q = pairs + 4 * (size_t)cur;
+			const float4 *q = pairs + 4 * RTX_IDX(cur, sc.pair_count);
 			const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
 			if (COUNT) visits += 2 * NR;
 			uint32_t mL = 0, mR = 0;
@@ -432,7 +433,7 @@ RTX_DEV void traverse_packet(const SceneDev &sc, const float4 *__restrict__ pair
 				/* entry = (ref, entry parameter with the ray mask in its 4 low mantissa bits) */
 				const uint32_t tbits = (__float_as_uint(r_first ? tL : tR) & ~0xFu) | (r_first ? mL : mR);
 				const uint2 e = make_uint2((uint32_t)(r_first ? refL : refR), tbits);
-				if (SMEM_STACK > 0 && sp < SMEM_STACK) s_stack[sp * stride] = e; else l_stack[sp - SMEM_STACK] = e;
+				if (SMEM_STACK > 0 && sp < SMEM_STACK) s_stack[sp * stride] = e; else l_stack[RTX_IDX(sp - SMEM_STACK, RTX_STACK_MAX - SMEM_STACK)] = e;
 				++sp;
 			}
 			cur = r_first ? refR : refL;
@@ -443,7 +444,7 @@ RTX_DEV void traverse_packet(const SceneDev &sc, const float4 *__restrict__ pair
 			const uint32_t first = enc >> 3, count = (enc & 7u) + 1u;
 			for (uint32_t k = 0; k < count; ++k) {
 				const uint32_t tri = first + k;
-				const float4 *q = sc.tris + 4 * (size_t)tri;
+				const float4 *q = sc.tris + 4 * RTX_IDX(tri, sc.num_tris);
 				const float4 t0 = __ldg(q), t1 = __ldg(q + 1), t2 = __ldg(q + 2), t3 = __ldg(q + 3);
 #pragma unroll
 				for (int r = 0; r < NR; ++r) {
@@ -453,7 +454,7 @@ RTX_DEV void traverse_packet(const SceneDev &sc, const float4 *__restrict__ pair
 					if (!triangle_test(t0, t1, t2, t3, o, d[r], cull[r], h)) continue;
 					if (!(h.dist < best[r].dist || (h.dist == best[r].dist && tri < best[r].tri))) continue;
 					if (sc.verify_leafbox) {
-						const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+						const float4 lo = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris)), hi = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris) + 1);
 						if (COUNT) ++lbtests;
 						if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), o, d[r], max_distance)) continue;
 					}
@@ -546,7 +547,7 @@ RTX_DEV void collect_frustum(const SceneDev &sc, const Frustum &f, int *__restri
 		float eL = 0.f, eR = 0.f;
 		if ((int)lane < n) {
 			const int pair = s_queue[(head + lane) % RTX_QCAP];
-			const float4 *q = sc.pairs + 4 * (size_t)pair;
+			const float4 *q = sc.pairs + 4 * RTX_IDX(pair, sc.pair_count);
 			const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
 			const bool pL = frustum_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, f, eL);
 			const bool pR = frustum_box(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, f, eR);
@@ -565,8 +566,8 @@ RTX_DEV void collect_frustum(const SceneDev &sc, const Frustum &f, int *__restri
 		if (tail - head + nI > RTX_QCAP || ncand + nF > cap) { ncand = -1; break; }
 		if (iL) s_queue[(tail + __popc(bIL & lt)) % RTX_QCAP] = refL;
 		if (iR) s_queue[(tail + __popc(bIL) + __popc(bIR & lt)) % RTX_QCAP] = refR;
-		if (fL) { const int k = ncand + __popc(bFL & lt); s_tmp[k] = ~(uint32_t)refL; s_tkey[k] = eL; }
-		if (fR) { const int k = ncand + __popc(bFL) + __popc(bFR & lt); s_tmp[k] = ~(uint32_t)refR; s_tkey[k] = eR; }
+		if (fL) { const int k = (int)RTX_IDX(ncand + __popc(bFL & lt), cap); s_tmp[k] = ~(uint32_t)refL; s_tkey[k] = eL; }
+		if (fR) { const int k = (int)RTX_IDX(ncand + __popc(bFL) + __popc(bFR & lt), cap); s_tmp[k] = ~(uint32_t)refR; s_tkey[k] = eR; }
 		tail += nI;
 		ncand += nF;
 		__syncwarp();
@@ -652,7 +653,7 @@ k_frustum_collect(const SceneDev sc, const Work w, const uint32_t *__restrict__ 
 			keep = true;
 			if ((enc & 7u) == 0u) {
 				const uint32_t tri = enc >> 3;
-				const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+				const float4 lo = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris)), hi = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris) + 1);
 				float e;
 				keep = frustum_box(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, f, e);
 			}
@@ -686,13 +687,13 @@ RTX_DEV int filter_candidates(const SceneDev &sc, const Frustum &f, const uint32
 			keep = true;
 			if ((enc & 7u) == 0u) {                       /* single-triangle leaf: its box is the triangle's leaf box */
 				const uint32_t tri = enc >> 3;
-				const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+				const float4 lo = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris)), hi = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris) + 1);
 				float e;
 				keep = frustum_box(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, f, e);
 			}
 		}
 		const unsigned b = __ballot_sync(0xffffffffu, keep);
-		if (keep) { const int k = m + __popc(b & lt); s_cand[k] = enc; s_key[k] = key; }
+		if (keep) { const int k = (int)RTX_IDX(m + __popc(b & lt), RTX_CCAP); s_cand[k] = enc; s_key[k] = key; }
 		m += __popc(b);
 	}
 	__syncwarp();
@@ -727,7 +728,7 @@ RTX_DEV void intersect_candidates(const SceneDev &sc, const uint32_t *__restrict
 		if (want) {
 			const uint32_t first = enc >> 3, last = first + (enc & 7u);
 			for (uint32_t tri = first; tri <= last; ++tri) {
-				const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+				const float4 lo = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris)), hi = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris) + 1);
 				uint32_t m = 0;
 #pragma unroll
 				for (int r = 0; r < NR; ++r) {
@@ -737,7 +738,7 @@ RTX_DEV void intersect_candidates(const SceneDev &sc, const uint32_t *__restrict
 					if (sl.tmin <= sl.tmax && sl.tmin < max_distance && sl.tmax > 0.0f) m |= 1u << r;   /* intersect_kernel.cl:41-60 */
 				}
 				if (!m) continue;
-				const float4 *q = sc.tris + 4 * (size_t)tri;
+				const float4 *q = sc.tris + 4 * RTX_IDX(tri, sc.num_tris);
 				const float4 t0 = __ldg(q), t1 = __ldg(q + 1), t2 = __ldg(q + 2), t3 = __ldg(q + 3);
 #pragma unroll
 				for (int r = 0; r < NR; ++r) {
@@ -1098,7 +1099,7 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 			if (__popc(__ballot_sync(full, descending)) < RTX_PT_MIN_DESCEND && __ballot_sync(full, has_ray && r.pend != RTX_PT_NONE) != 0u) break;
 			if (__ballot_sync(full, descending) == 0u) break;
 			if (descending) {
-				const float4 *q = sc.pairs + 4 * (size_t)r.cur;
+				const float4 *q = sc.pairs + 4 * RTX_IDX(r.cur, sc.pair_count);
 				const f4x2 qa = ldg256(q), qb = ldg256(q + 2);
 				const float4 q0 = qa.a, q1 = qa.b, q2 = qb.a, q3 = qb.b;
 				if (COUNT) visits += 2;
@@ -1115,7 +1116,7 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 					const bool r_first = hitR && (!hitL || R.tmin < L.tmin);
 					if (hitL && hitR) {
 						const uint2 e = make_uint2((uint32_t)(r_first ? refL : refR), __float_as_uint(r_first ? cL : cR));
-						if (SMEM_STACK > 0 && r.sp < SMEM_STACK) s_stack[r.sp * stride] = e; else l_stack[r.sp - SMEM_STACK] = e;
+						if (SMEM_STACK > 0 && r.sp < SMEM_STACK) s_stack[r.sp * stride] = e; else l_stack[RTX_IDX(r.sp - SMEM_STACK, RTX_STACK_MAX - SMEM_STACK)] = e;
 						++r.sp;
 					}
 					next = r_first ? refR : refL;
@@ -1134,14 +1135,14 @@ k_trace_persistent(const SceneDev sc, const RayWork rw, const Work pw, Counters 
 			const uint32_t first = enc >> 3, count = (enc & 7u) + 1u;
 			for (uint32_t k = 0; k < count; ++k) {
 				const uint32_t tri = first + k;
-				const float4 *q = sc.tris + 4 * (size_t)tri;
+				const float4 *q = sc.tris + 4 * RTX_IDX(tri, sc.num_tris);
 				TriHit h;
 				if (COUNT) ++tests;
 				const f4x2 ta = ldg256(q), tb = ldg256(q + 2);
 				if (!triangle_test(ta.a, ta.b, tb.a, tb.b, r.o, r.d, r.cull, h)) continue;
 				if (!(h.dist < r.best.dist || (h.dist == r.best.dist && tri < r.best.tri))) continue;
 				if (sc.verify_leafbox) {
-					const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+					const float4 lo = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris)), hi = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris) + 1);
 					if (COUNT) ++lbtests;
 					if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), r.o, r.d, r.max_distance)) continue;
 				}
@@ -1253,7 +1254,7 @@ __device__ __noinline__ bool walk_reference_any(const SceneDev &sc, f3 o, f3 d, 
 			i += node_count;
 		} else {
 			if (node_count == 1) {
-				const float4 *q = sc.tris + 4 * (size_t)tri;
+				const float4 *q = sc.tris + 4 * RTX_IDX(tri, sc.num_tris);
 				TriHit h;
 				if (triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, __int_as_float(0x7f800000), h)) return true;
 				++tri;
@@ -1278,7 +1279,7 @@ RTX_DEV int ao_entry_pair(const SceneDev &sc, f3 p, float max_distance)
 	const f3 lo = make_f3(p.x - R, p.y - R, p.z - R), hi = make_f3(p.x + R, p.y + R, p.z + R);
 	int cur = 0;
 	for (;;) {
-		const float4 *q = sc.pairs + 4 * (size_t)cur;
+		const float4 *q = sc.pairs + 4 * RTX_IDX(cur, sc.pair_count);
 		const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
 		const bool inL = q0.x <= hi.x && q0.w >= lo.x && q0.y <= hi.y && q1.x >= lo.y && q0.z <= hi.z && q1.y >= lo.z;
 		const bool inR = q2.x <= hi.x && q2.w >= lo.x && q2.y <= hi.y && q3.x >= lo.y && q2.z <= hi.z && q3.y >= lo.z;
@@ -1299,7 +1300,7 @@ RTX_DEV bool any_hit(const SceneDev &sc, bool ordered_ok, int entry, f3 o, f3 d,
 	int sp = 0, cur = entry;
 	for (;;) {
 		while (cur >= 0) {
-			const float4 *q = sc.pairs + 4 * (size_t)cur;
+			const float4 *q = sc.pairs + 4 * RTX_IDX(cur, sc.pair_count);
 			const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
 			const Slab L = slab_interval<false, 4>(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, id);
 			const Slab R = slab_interval<false, 4>(q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, o, id);
@@ -1308,18 +1309,18 @@ RTX_DEV bool any_hit(const SceneDev &sc, bool ordered_ok, int entry, f3 o, f3 d,
 			if (!(hitL || hitR)) goto pop;
 			const int refL = __float_as_int(q1.z), refR = __float_as_int(q3.z);
 			const bool r_first = hitR && (!hitL || R.tmin < L.tmin);
-			if (hitL && hitR) stack[sp++] = r_first ? refL : refR;
+			if (hitL && hitR) stack[RTX_IDX(sp++, RTX_STACK_MAX)] = r_first ? refL : refR;
 			cur = r_first ? refR : refL;
 		}
 		{
 			const uint32_t enc = ~(uint32_t)cur;
 			const uint32_t first = enc >> 3, last = first + (enc & 7u);
 			for (uint32_t tri = first; tri <= last; ++tri) {
-				const float4 *q = sc.tris + 4 * (size_t)tri;
+				const float4 *q = sc.tris + 4 * RTX_IDX(tri, sc.num_tris);
 				TriHit h;
 				if (!triangle_test(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, __int_as_float(0x7f800000), h)) continue;
 				if (sc.verify_leafbox) {
-					const float4 lo = __ldg(sc.leafbox + 2 * (size_t)tri), hi = __ldg(sc.leafbox + 2 * (size_t)tri + 1);
+					const float4 lo = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris)), hi = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris) + 1);
 					if (!aabb_exact(make_f3(lo.x, lo.y, lo.z), make_f3(hi.x, hi.y, hi.z), o, d, max_distance)) continue;
 				}
 				return true;
@@ -1423,14 +1424,14 @@ k_ambient_occlusion(const SceneDev sc, const Work w, const AoParams ao)
 	const f3 o = make_f3(0.0f, 0.0f, 2.0f);
 	const f3 d = primary_dir(w.cam, x, y);
 	/* the hit point as triangle_test computed it (:71-85) */
-	const float4 *q = sc.tris + 4 * (size_t)tri;
+	const float4 *q = sc.tris + 4 * RTX_IDX(tri, sc.num_tris);
 	const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
 	const f3 a = make_f3(q0.x, q0.y, q0.z), nrm = make_f3(q0.w, q1.w, q2.w);
 	const f3 w0 = sub3(o, a);
 	const float r = rn_div(-dot3(nrm, w0), dot3(nrm, d));
 	const f3 point = make_f3(rn_add(o.x, rn_mul(r, d.x)), rn_add(o.y, rn_mul(r, d.y)), rn_add(o.z, rn_mul(r, d.z)));
 	/* the smooth normal (:118-127) */
-	const float4 n0 = __ldg(sc.tnormals + 3 * (size_t)tri), n1 = __ldg(sc.tnormals + 3 * (size_t)tri + 1), n2 = __ldg(sc.tnormals + 3 * (size_t)tri + 2);
+	const float4 n0 = __ldg(sc.tnormals + 3 * RTX_IDX(tri, sc.num_tris)), n1 = __ldg(sc.tnormals + 3 * RTX_IDX(tri, sc.num_tris) + 1), n2 = __ldg(sc.tnormals + 3 * RTX_IDX(tri, sc.num_tris) + 2);
 	const float b0 = rn_sub(rn_sub(1.0f, st.x), st.y), b1 = st.x, b2 = st.y;
 	const f3 normal = normalize3(make_f3(rn_add(rn_add(rn_mul(n0.x, b0), rn_mul(n1.x, b1)), rn_mul(n2.x, b2)),
 	                                     rn_add(rn_add(rn_mul(n0.y, b0), rn_mul(n1.y, b1)), rn_mul(n2.y, b2)),

@@ -39,7 +39,7 @@ ABI_SYMBOLS = (
     "rtx_probe_bandwidth", "rtx_resize_u8_async", "rtx_deinterleave_u8_async", "rtx_render_download",
     "rtx_upload_mesh", "rtx_download_tree", "rtx_build_stats", "rtx_download_normals",
     "rtx_resize_u8_to_async", "rtx_store_tiles_async", "rtx_adopt_u8", "rtx_peer_alloc", "rtx_peer_open", "rtx_peer_close",
-    "rtx_peer_free", "rtx_host_register", "rtx_host_unregister", "rtx_phase_ms", "rtx_copy_to_host", "rtx_bind_output_image", "rtx_render_store", "rtx_render_store_async",
+    "rtx_peer_free", "rtx_host_register", "rtx_host_unregister", "rtx_phase_ms", "rtx_copy_to_host", "rtx_bind_output_image", "rtx_render_store", "rtx_render_store_async", "rtx_debug_bounds",
 )
 
 
@@ -177,6 +177,8 @@ def load_library():
     lib.rtx_render_store.argtypes = [vp, vp]
     lib.rtx_render_store_async.restype = C.c_int
     lib.rtx_render_store_async.argtypes = [vp, vp, vp]
+    lib.rtx_debug_bounds.restype = C.c_int
+    lib.rtx_debug_bounds.argtypes = [vp, C.POINTER(C.c_uint * 4)]
     lib.rtx_copy_to_host.restype = C.c_int
     lib.rtx_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
     lib.rtx_phase_ms.restype = C.c_int
@@ -489,6 +491,12 @@ class CudaHost:
         assert out.flags.c_contiguous
         self._ck(self._lib.rtx_copy_to_host(self._ctx, C.c_void_p(out.ctypes.data), C.c_void_p(device_ptr), out.nbytes))
         return out
+
+    def debug_bounds(self):
+        """Bounds-checked debug build only: (violations, line, index, limit) since the last call."""
+        out = (C.c_uint * 4)()
+        self._ck(self._lib.rtx_debug_bounds(self._ctx, C.byref(out)))
+        return tuple(int(x) for x in out)
 
     def phase_ms(self) -> dict:
         """Device time per launch group of the last frame (needs TUNE_PHASE_TIMING)."""

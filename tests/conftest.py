@@ -50,6 +50,11 @@ def rays_golden():
 
 
 @pytest.fixture(scope="session")
+def special_rays_golden():
+    return load_golden("soup_special_rays.npz")
+
+
+@pytest.fixture(scope="session")
 def quad_golden():
     return load_golden("quad_33x17.npz")
 

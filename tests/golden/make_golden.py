@@ -15,6 +15,8 @@ restatement or the CUDA path.  Outputs (small, committed):
   scenes.json         sha256 digests of the reference builder's arrays + bunny known answers
   soup_sah.npz        the soup's tree from the reference's SAH builder (`-r sah`, bvh.cc:178-236) as upload arrays +
                       its render; `python tests/golden/make_golden.py sah` writes only this file
+  soup_special_rays.npz  3072 rays with zero / subnormal / tiny / huge direction components from origins exactly on
+                      leaf-box planes (`python tests/golden/make_golden.py special` writes only this file)
   soup_ao.npz         the soup with ambient occlusion (uniform rings 3, random 3, random 1 with a longer reach);
                       `python tests/golden/make_golden.py ao` writes only this file
 """
@@ -89,8 +91,45 @@ def make_sah():
     print("soup_sah.npz written (%d nodes)" % sc.nodes.size)
 
 
+def make_special():
+    """Rays at the edge of IEEE arithmetic: direction components that are zero, subnormal (1/d overflows to inf below
+    2^-128, is finite just above), the smallest and the largest normals, from origins that lie EXACTLY on planes of leaf
+    boxes (so (bb - o) * (1/d) is 0 * inf = NaN there) and on vertices.  Hits of the reference's kernel text."""
+    v, f = scenes.random_soup(300, seed=11)
+    sc = ref_scene(v, f)
+    rng = np.random.default_rng(77)
+    n = 3072
+    leaf = np.flatnonzero(sc.nodes == 1)
+    pick = rng.choice(leaf, n)
+    lo, hi = sc.aabbs[2 * pick, :3], sc.aabbs[2 * pick + 1, :3]
+    o = np.zeros((n, 4), np.float32)
+    d = np.zeros((n, 4), np.float32)
+    o[:, :3] = lo + (hi - lo) * rng.uniform(-0.5, 1.5, (n, 3)).astype(np.float32)
+    d[:, :3] = rng.normal(size=(n, 3)).astype(np.float32)
+    ax = rng.integers(0, 3, n)
+    rows = np.arange(n)
+    side = rng.random(n) < 0.5
+    o[rows, ax] = np.where(side, lo[rows, ax], hi[rows, ax])                  # exactly on a plane of the picked leaf box
+    special = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-40, -1e-40, 2.9e-39, -2.9e-39, 2.95e-39, 5e-39, -5e-39, 1.17549435e-38,
+                        -1.17549435e-38, 1.2e-38, 3e-38, 1e-30, -1e-30, 3.4e38, -3.4e38], np.float32)
+    d[rows, ax] = special[rng.integers(0, special.size, n)]
+    two = rng.random(n) < 0.25                                                # a second special component
+    ax2 = (ax + 1 + rng.integers(0, 2, n)) % 3
+    d[rows[two], ax2[two]] = special[rng.integers(0, special.size, int(two.sum()))]
+    o[:64, :3] = sc.vertices[sc.faces[:64], :3]                               # origins on vertices
+    # (no NaN / inf components: with them the reference's triangle test "hits" without ever updating the closest
+    # hit, and the kernel then reads an Intersection it never initialised -- intersect_kernel.cl:106-112, 292-299)
+    fid, dist = po.ref_trace_rays(sc, o, d, 100000.0)
+    fid2, dist2 = po.ref_trace_rays(sc, o, d, 0.75)
+    np.savez_compressed(os.path.join(OUT, "soup_special_rays.npz"), verts=v, faces=f, origins=o, dirs=d, face_id=fid, distance=dist,
+                        face_id_d075=fid2, distance_d075=dist2)
+    print("soup_special_rays.npz written: %d rays, %d hits" % (n, int((fid != po.NO_HIT).sum())))
+
+
 def main():
     assert po.ref() is not None, "oracle/_ref/libref_oracle.so missing: run make -C oracle"
+    if sys.argv[1:] == ["special"]:
+        return make_special()
     if sys.argv[1:] == ["ao"]:
         return make_ao()
     if sys.argv[1:] == ["sah"]:
@@ -151,6 +190,7 @@ def main():
                   fh, indent=1, sort_keys=True)
     make_ao()
     make_sah()
+    make_special()
     print("golden vectors written to", OUT)
 
 

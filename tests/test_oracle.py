@@ -40,6 +40,18 @@ def test_port_matches_golden_rays(po, soup_scene, rays_golden):
     assert (g["dirs"][-64:, :3] == 0).any(axis=1).all()
 
 
+def test_port_matches_golden_special_direction_rays(po, soup_scene, special_rays_golden):
+    """zero / subnormal / smallest-normal / huge direction components from origins exactly on leaf-box planes"""
+    g = special_rays_golden
+    for md, key in ((100000.0, ""), (0.75, "_d075")):
+        r = po.trace_rays(soup_scene, g["origins"], g["dirs"], md)
+        assert np.array_equal(r.face_id, g["face_id" + key])
+        assert np.array_equal(_bits(r.distance), _bits(g["distance" + key]))
+    d = np.abs(g["dirs"][:, :3])
+    assert ((d > 0) & (d < 1.17549435e-38)).any() and (d == 0).any()        # subnormal and zero components are in the set
+    assert (g["face_id"] != po.NO_HIT).sum() > 500                            # ... and the set still produces hits
+
+
 def test_port_matches_golden_quad_odd_size(po, scene_mod, quad_golden, golden_meta):
     g = quad_golden
     sc = scene_mod.scene_from_mesh(g["verts"], g["faces"])

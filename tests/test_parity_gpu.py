@@ -295,6 +295,26 @@ def test_arbitrary_rays_golden(po, soup_scene, rays_golden):
             assert h.trace_rays(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32))[0].size == 0
 
 
+@pytest.mark.parametrize("incoherent,leaf", [(1, 1), (0, 1), (1, 4), (0, 8)])
+def test_special_direction_rays_golden(soup_scene, special_rays_golden, incoherent, leaf):
+    """Rays with zero, subnormal (1/d = inf below 2^-128), smallest-normal and huge direction components from origins exactly
+    on leaf-box planes (0 * inf = NaN slabs): only the literal form of the slab test reproduces the reference there, so
+    ray_is_plain (rtx_device.cuh) must route them to walk_reference.  Hits of the reference's own kernel text."""
+    host = require_gpu()
+    g = special_rays_golden
+    rt = host.RayTracer(host.Options(width=32, height=32, nSuperSamples=1))
+    with host.CudaHost(rt) as h:
+        h.set_tunable(host.TUNE_INCOHERENT_KERNEL, incoherent)
+        h.set_tunable(host.TUNE_LEAF_SIZE, leaf)
+        h.upload_scene(soup_scene)
+        for md, key in ((100000.0, ""), (0.75, "_d075")):
+            fid, dist = h.trace_rays(g["origins"], g["dirs"], md)
+            bad = np.flatnonzero(fid != g["face_id" + key])
+            assert bad.size == 0, "ray %d: origin %s dir %s -> %d, reference %d" % (
+                bad[0], g["origins"][bad[0]], g["dirs"][bad[0]], fid[bad[0]], g["face_id" + key][bad[0]])
+            assert np.array_equal(dist.view(np.uint32), g["distance" + key].view(np.uint32))
+
+
 def test_random_ray_batch(po, sibenik_scene):
     """Config C5: rays generated on the device from the counter hash == the oracle's generator; a 2^16 prefix
     is checked ray by ray, a 2^22 batch through split-invariant checksums."""

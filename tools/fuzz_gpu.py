@@ -6,6 +6,10 @@ arbitrary rays (both kernels vs the literal walk), ambient occlusion against the
 device-built BVH (rtx_upload_mesh) against the host builder's arrays.
 
 usage: python tools/fuzz_gpu.py [first_seed=0] [count=40]
+       RTX_B200_LIB=$PWD/opencl_raytracer_b200/lib/librtx_b200_dbg.so python tools/fuzz_gpu.py ...   (after `make -C
+       opencl_raytracer_b200/csrc debug`): the same run against the bounds-checked build -- every device-side index into the
+       scene arrays, stacks, queues and candidate lists is range-checked (the stand-in for compute-sanitizer, which is
+       closed on this pool); a violation is reported with its source line.
 """
 import os
 import sys
@@ -198,6 +202,43 @@ def main():
             if nb:
                 bad += nb
                 print("  MISMATCH seed %d tile partition (world %d) / render_download: %d pixels" % (seed, world, nb), flush=True)
+        # the collective-free tile paths: every emulated rank stores its share straight into one image (device and mapped host memory)
+        if seed % 3 == 1:
+            world = int(rng.choice([2, 3, 4]))
+            shared = np.full((rt.totalHeight, rt.totalWidth), -1.0, np.float32)
+            alias = host.host_register(shared)
+            ctxs = [host.CudaHost(rt, jitter_seed=jitter, tile_rank=r, tile_world=world) for r in range(world)]
+            for c in ctxs:
+                c.upload_scene(sc)
+                if seed % 2:
+                    c.set_tunable(host.TUNE_FRUSTUM, 1)          # the packet kernel sends finished tiles itself
+                c.render_store(alias)
+            nb = int(((shared != base[1]) & ~(np.isnan(shared) & np.isnan(base[1]))).sum())
+            if 32 % rt.n == 0:
+                d_u8, _ = ctxs[0].peer_alloc(w * hgt)
+                for c in ctxs:
+                    c.set_tunable(host.TUNE_FRUSTUM, -1)
+                    c()
+                    c.resize_u8_to_async(d_u8)
+                    c.synchronize()
+                ctxs[0].adopt_u8(d_u8)
+                nb += int((ctxs[0].download_u8() != host.host_resize(base[1], rt)).sum())
+                ctxs[0].peer_free(d_u8)
+            host.host_unregister(shared)
+            for c in ctxs:
+                c.close()
+            if nb:
+                bad += nb
+                print("  MISMATCH seed %d direct stores (world %d): %d pixels" % (seed, world, nb), flush=True)
+        # bounds-checked debug build (RTX_B200_LIB=.../librtx_b200_dbg.so): no index left its array during this seed
+        try:
+            with host.CudaHost(rt) as h:
+                viol = h.debug_bounds()
+            if viol[0]:
+                bad += viol[0]
+                print("  BOUNDS seed %d: %d out-of-range indices, first at rtx_kernels.cuh:%d (index %d, limit %d)" % (seed, *viol), flush=True)
+        except host.RtxError:
+            pass                                     # release build
         hitfrac = float((base[2][0] != host.NO_HIT).mean())
         print("seed %3d %-10s scale %-6g %4d tris depth %2d  %dx%d s=%d f=%.1f jitter %d  hit %.2f  %s" % (
             seed, kind, scale, sc.num_triangles, base[3], w, hgt, ss, focal, int(jitter != 0), hitfrac, "ok" if bad == 0 else "BAD (%d)" % bad), flush=True)
