@@ -290,6 +290,45 @@ def extra_c4(local_rank, peak):
     return out
 
 
+def extra_irregular(local_rank):
+    """The frame of the headline workload on an IRREGULAR scene (scenes.cluttered_interior: 0.98 M triangles from sub-pixel
+    to screen-filling): what the frustum front end is worth when tile lists overflow, next to the regular stand-in."""
+    from opencl_raytracer_b200 import host, scene, scenes
+    from oracle import pyoracle as po
+    v, f = scenes.cluttered_interior()
+    sc = scene.scene_from_mesh(v, f, name="cluttered_interior")
+    rt = host.RayTracer(host.Options(width=3840, height=2160, nSuperSamples=16))
+    tw, th = rt.totalWidth, rt.totalHeight
+    out = {"scene": "scenes.cluttered_interior(): %d triangles, hundreds of finely tessellated spheres in a room with noise-displaced walls"
+                    % sc.num_triangles, "rays": tw * th}
+    for name, tun in (("auto", {}), ("per_ray_traversal", {host.TUNE_FRUSTUM: 0})):
+        with host.CudaHost(rt, device=local_rank) as h:
+            for k, val in tun.items():
+                h.set_tunable(k, val)
+            h.upload_scene(sc)
+            best = 1e9
+            for _ in range(3):
+                h()
+                best = min(best, h.stats()["kernel_ms"])
+            out[name] = {"kernel_ms": best, "Mrays/s": tw * th / best / 1e3}
+            if name == "auto":
+                h.set_tunable(host.TUNE_COUNTERS, 1)
+                h()
+                st = h.stats()
+                out[name].update({"packets_through_the_overflow_launch": st["packet_overflows"],
+                                  "share_of_packets": st["packet_overflows"] / (tw * th / 128.0),
+                                  "leaf_box_tests_per_ray": st["leafbox_tests"] / (tw * th), "triangle_tests_per_ray": st["tri_tests"] / (tw * th)})
+                h.set_tunable(host.TUNE_COUNTERS, 0)
+                h()
+                img = h.download()
+                rows = (135, th, 270)
+                ys = list(range(*rows))
+                ref = po.render(sc, tw, th, 1.0, True, rows=rows, want_ids=False, want_counters=True)
+                out["parity"] = {"rows_vs_oracle": len(ys), "pixel_mismatches": int((img[ys].view(np.uint32) != ref.image[ys].view(np.uint32)).sum())}
+                out["exhaustive_walk_V_T"] = [ref.counters["V"], ref.counters["T"]]
+    return out
+
+
 def extra_c5(local_rank, sc, peak):
     """BASELINE config 5 inside the default line (N = 1): 2^28 random rays (counter-hash generator, seed 1234) against the
     stand-in tree; value = best device time of 3 batches; parity = a 2^16 prefix against the oracle + checksums."""
@@ -818,6 +857,7 @@ def main():
         peak_hbm = load_peaks()[0]
         extras["c5"] = extra_c5(local_rank, sc, peak_hbm) if args.workload == "c3" else None
         extras["c4"] = extra_c4(local_rank, peak_hbm) if args.workload == "c3" else None
+        extras["irregular_interior"] = extra_irregular(local_rank) if args.workload == "c3" else None
         extras["reference_algorithm_on_gpu"]["what"] = ("k_render_exhaustive: the reference kernel's own algorithm (one thread per pixel, "
                                                         "stackless pre-order walk, no culling) compiled for sm_100a")
 

@@ -237,6 +237,42 @@ def sibenik_standin(detail: float = 1.0):
 
 # ------------------------------------------------------------ small cases ---
 
+def cluttered_interior(seed: int = 3, nobjects: int = 420, detail: int = 4):
+    """An IRREGULAR, finely tessellated interior (the counter-example to the stand-in's regular parametric grids): a
+    closed room around the camera whose walls, floor and ceiling are jittered grids displaced by noise, filled with
+    `nobjects` icospheres of random size at random places -- many of them close to the camera, tessellated `detail`
+    levels deep (20 * 4^detail triangles each), so that triangles range from sub-pixel to screen-filling and a 32x32-pixel
+    tile sees anything from a handful to thousands of leaves.  ~0.5 M triangles at the defaults."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    lo, hi = np.array([-6.0, -3.0, -16.0]), np.array([6.0, 5.0, 3.0])
+    n = 90
+    for axis in range(3):
+        a1, a2 = (axis + 1) % 3, (axis + 2) % 3
+        for side, flip in ((0, False), (1, True)):                          # normals point into the room
+            u = np.linspace(0, 1, n + 1)
+            uu, vv = np.meshgrid(u, u, indexing="ij")
+            ju = uu + (rng.uniform(-0.35, 0.35, uu.shape) / n) * ((uu > 0) & (uu < 1))        # jittered, borders kept
+            jv = vv + (rng.uniform(-0.35, 0.35, vv.shape) / n) * ((vv > 0) & (vv < 1))
+            bump = 0.12 * np.sin(7.0 * ju + 3.0 * axis) * np.sin(5.0 * jv + side) + rng.normal(0, 0.015, uu.shape)
+            bump = bump * ((uu > 0) & (uu < 1) & (vv > 0) & (vv < 1))                           # the room stays closed
+            p = [None, None, None]
+            p[axis] = (hi[axis] if side else lo[axis]) + (-bump if side else bump)
+            p[a1] = lo[a1] + ju * (hi[a1] - lo[a1])
+            p[a2] = lo[a2] + jv * (hi[a2] - lo[a2])
+            parts.append((np.stack(p, -1).reshape(-1, 3), _grid_faces(n, n, flip=flip)))
+    for k in range(nobjects):
+        z = -rng.uniform(0.2, 15.0)
+        spread = 0.35 * (2.0 - z) + 0.3                                     # roughly inside the view cone
+        c = np.array([rng.uniform(-spread, spread), rng.uniform(-0.6 * spread, 0.6 * spread), z])
+        c = np.clip(c, lo + 0.3, hi - 0.3)
+        r = float(min(rng.lognormal(-2.0, 0.8), 0.9)) * (0.35 + 0.12 * abs(z))          # nearer objects are smaller
+        lvl = int(np.clip(detail + rng.integers(-2, 1), 1, 6))
+        parts.append(icosphere(c, r, lvl))
+    v, f = _merge(parts)
+    return _finish(v, f)
+
+
 def random_soup(ntris: int, seed: int = 1, extent: float = 1.5, size: float = 0.35, big: int = 2):
     """Random triangle soup in front of the camera (z in [-extent, extent]); the
     first `big` triangles are large so that rays see several layers."""

@@ -132,3 +132,38 @@ def test_c5_random_ray_batch(po, sibenik_scene):
                 assert (sum(p[0] for p in parts), sum(p[1] for p in parts)) == sums[1]
     assert sums[1] == sums[0], "the two arbitrary-ray kernels disagree on the 2^28-ray checksums: %s vs %s" % (sums[1], sums[0])
     assert 0.85 < sums[1][0] / total < 0.99                      # rays start inside a closed room: most of them hit
+
+
+@pytest.mark.parametrize("frustum", [-1, 1], ids=["auto", "frustum_forced"])
+def test_cluttered_interior_irregular_tessellation(po, scene_mod, frustum):
+    """The counter-example to the stand-in's regular grids: 0.98 M triangles from sub-pixel to screen-filling (hundreds of
+    finely tessellated spheres in a room with noise-displaced walls), 3840x2160 rays.  With the frustum front end forced,
+    tiles whose candidate list overflows (> 192 leaves) fall back to the per-ray traversal launch (MODE 2): both paths of
+    the frame must give the literal walk's result."""
+    host = require_gpu()
+    from opencl_raytracer_b200 import scenes
+    v, f = scenes.cluttered_interior()
+    sc = scene_mod.scene_from_mesh(v, f, name="cluttered_interior")
+    assert sc.num_triangles > 900000
+    rt = host.RayTracer(host.Options(width=1920, height=1080, nSuperSamples=4))
+    tw, th = rt.totalWidth, rt.totalHeight
+    with host.CudaHost(rt) as h:
+        h.set_tunable(host.TUNE_FRUSTUM, frustum)
+        h.set_tunable(host.TUNE_RECORD_HITS, 1)
+        h.set_tunable(host.TUNE_COUNTERS, 1)
+        h.upload_scene(sc)
+        h()
+        st = h.stats()
+        img = h.download()
+        fid, dist = h.download_hits()
+    if frustum == 1:
+        assert st["packet_overflows"] > 0, "no tile list overflowed: the scene does not exercise the overflow launch"
+        assert st["leafbox_tests"] > 0                     # ... and other tiles did go through their lists
+    rows = (20, th, 40)
+    ys = list(range(*rows))
+    ref = po.render(sc, tw, th, 1.0, True, rows=rows)
+    assert int((fid[ys] != ref.face_id[ys]).sum()) == 0
+    assert _same(dist[ys], ref.distance[ys]) and _same(img[ys], ref.image[ys])
+    img_x, fid_x, dist_x, _ = _render_with_hits(host, rt, sc, host.KERNEL_EXHAUSTIVE)
+    assert np.array_equal(fid, fid_x), "%d hit ids differ from the literal walk" % int((fid != fid_x).sum())
+    assert _same(dist, dist_x) and _same(img, img_x)
