@@ -79,7 +79,7 @@ struct rtx_ctx {
 	/* scene */
 	bool uploaded = false;
 	SceneDev sc{};
-	DevBuf d_pairs, d_tris, d_leafbox, d_tnormals, d_ref_nodes, d_ref_aabbs;
+	DevBuf d_pairs, d_tris, d_leafbox, d_pleafbox, d_tnormals, d_ref_nodes, d_ref_aabbs;
 	DevBuf t_faces, t_verts, t_vnormals, t_scan;   /* upload staging, kept between uploads */
 	DevBuf t_build, d_triangles;                   /* rtx_upload_mesh: builder work space; leaf order -> input face id */
 	DevBuf t_parent;                               /* device flatten: parent link of every node pair (k_slack_leaves) */
@@ -624,7 +624,7 @@ void rtx_destroy(rtx_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
-	DevBuf *bufs[] = { &c->t_parent, &c->t_build, &c->d_triangles, &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
+	DevBuf *bufs[] = { &c->t_parent, &c->t_build, &c->d_triangles, &c->t_faces, &c->t_verts, &c->t_vnormals, &c->t_scan, &c->d_pairs, &c->d_pleafbox, &c->d_tris, &c->d_leafbox, &c->d_tnormals, &c->d_ref_nodes, &c->d_ref_aabbs,
 	                   &c->d_image, &c->d_image_full, &c->d_face_id, &c->d_dist, &c->d_u8, &c->d_counter, &c->d_counters, &c->d_sums, &c->d_lists, &c->d_slists, &c->d_raytab,
 	                   &c->d_hit_st, &c->d_ao_ring, &c->d_tile_done };
 	for (DevBuf *b : bufs) b->release();
@@ -727,7 +727,7 @@ static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nver
 			c->d_ref_nodes.as<uint32_t>(), c->d_ref_aabbs.as<float4>(), first_leaf, pair_idx,
 			c->t_faces.as<uint32_t>(), c->t_verts.as<float4>(), c->t_vnormals.as<float4>(), n, (uint32_t)pair_stride, K,
 			c->d_pairs.as<float4>(), c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>(), (uint32_t)nverts, res,
-			c->t_parent.as<uint32_t>());
+			c->t_parent.as<uint32_t>(), c->d_pleafbox.as<float4>());
 		CUU(cudaGetLastError());
 		CUU(cudaMemcpyAsync(&c->h_tree, res, sizeof(TreeResult), cudaMemcpyDeviceToHost, st));
 		CUU(cudaStreamSynchronize(st));
@@ -776,7 +776,8 @@ static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nver
 		CUU(cudaMemcpyAsync(c->d_pairs.p, flat.pairs.data(), flat.pairs.size() * 16, cudaMemcpyHostToDevice, st));
 		k_build_triangles<<<(unsigned)((ntris + 255) / 256), 256, 0, st>>>(
 			c->t_faces.as<uint32_t>(), c->t_verts.as<float4>(), c->t_vnormals.as<float4>(), c->t_scan.as<uint32_t>(),
-			c->d_ref_aabbs.as<float4>(), (uint32_t)ntris, c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>());
+			c->d_ref_aabbs.as<float4>(), (uint32_t)ntris, c->d_tris.as<float4>(), c->d_leafbox.as<float4>(), c->d_tnormals.as<float4>(),
+			c->d_pleafbox.as<float4>());
 		CUU(cudaGetLastError());
 		CUU(cudaStreamSynchronize(st));     /* flat's vectors die at the end of this block */
 	}
@@ -812,6 +813,7 @@ static int upload_finish(rtx_ctx *c, size_t nfaceidx, size_t nnodes, size_t nver
 	c->sc.pairs = c->d_pairs.as<float4>();
 	c->sc.tris = c->d_tris.as<float4>();
 	c->sc.leafbox = c->d_leafbox.as<float4>();
+	c->sc.pleafbox = c->d_pleafbox.as<float4>();
 	c->sc.tnormals = c->d_tnormals.as<float4>();
 	c->sc.ref_nodes = c->d_ref_nodes.as<uint32_t>();
 	c->sc.ref_aabbs = c->d_ref_aabbs.as<float4>();
@@ -857,6 +859,7 @@ int rtx_upload(rtx_ctx *c, const uint32_t *faces, size_t nfaceidx, const uint32_
 	CUU(c->d_ref_aabbs.alloc(nnodes * 32));
 	CUU(c->d_tris.alloc(ntris * 64));
 	CUU(c->d_leafbox.alloc(ntris * 32));
+	CUU(c->d_pleafbox.alloc(ntris * 32));
 	CUU(c->d_tnormals.alloc(ntris * 48));
 	CUU(cudaMemcpyAsync(c->t_faces.p, faces, nfaceidx * 4, cudaMemcpyHostToDevice, st));
 	CUU(cudaMemcpyAsync(c->t_verts.p, verts16, nverts * 16, cudaMemcpyHostToDevice, st));
@@ -893,6 +896,7 @@ int rtx_upload_mesh(rtx_ctx *c, const float *verts16, size_t nverts, const uint3
 	CUU(c->d_triangles.alloc((size_t)N * 4));
 	CUU(c->d_tris.alloc((size_t)N * 64));
 	CUU(c->d_leafbox.alloc((size_t)N * 32));
+	CUU(c->d_pleafbox.alloc((size_t)N * 32));
 	CUU(c->d_tnormals.alloc((size_t)N * 48));
 	/* work space: input faces, per-triangle centroid / lo / hi, two copies of (ids, segments, accumulators), scan, partials, flags */
 	const uint32_t per_block = RTX_BVH_BLOCK * RTX_BVH_ITEMS, nblocks = (N + per_block - 1) / per_block;

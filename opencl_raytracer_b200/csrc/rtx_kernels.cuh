@@ -15,6 +15,7 @@
  *             (staged in shared memory), the rest depth-first.
  *   tris      4 x float4 per triangle in leaf order (rtx_device.cuh)
  *   leafbox   2 x float4 per triangle: its reference leaf AABB (min, max)
+ *   pleafbox  the same with the ray-independent terms of a PRIMARY ray's tests folded in (candidate-list kernel)
  *   tnormals  3 x float4 per triangle: the three corner normals, pre-gathered
  *   ref_nodes / ref_aabbs   the reference's own arrays, for the literal
  *             stackless walk (exhaustive kernel, NaN-slab rays, deep trees)
@@ -26,6 +27,8 @@ struct SceneDev {
 	const float4 *pairs;      /* 4 octant copies, each num_pairs * 4 float4 (copy 0 = unswapped) */
 	const float4 *tris;
 	const float4 *leafbox;
+	const float4 *pleafbox;   /* the leaf boxes again, prepared for PRIMARY rays (camera at (0,0,2)): (lo.x, lo.y, lo.z - 2, A),
+	                             (hi.x, hi.y, hi.z - 2, 0) with A = -dot(n, o - a) of the triangle (triangle_test_primary) */
 	const float4 *tnormals;
 	const uint32_t *ref_nodes;
 	const float4 *ref_aabbs;
@@ -509,8 +512,11 @@ struct Frustum { float u0, u1, v0, v1, margin; };   /* ray = (0,0,2) + s * (u, v
 RTX_DEV Frustum make_frustum(const Camera &cam, float X0, float Y0, float PW, float PH, float scene_scale)
 {
 	Frustum f;
-	const float ua = X0 / cam.a - cam.w_over_2a, ub = (X0 + PW) / cam.a - cam.w_over_2a;
-	const float va = -(Y0 / cam.a - cam.h_over_2a), vb = -((Y0 + PH) / cam.a - cam.h_over_2a);
+	/* a conservative bound, not a deciding value: a reciprocal and four products instead of four IEEE divisions (2 % of
+	 * the list kernel's instructions); the 1e-5 widening below is two orders above the difference */
+	const float inv_a = __frcp_rn(cam.a);
+	const float ua = X0 * inv_a - cam.w_over_2a, ub = (X0 + PW) * inv_a - cam.w_over_2a;
+	const float va = -(Y0 * inv_a - cam.h_over_2a), vb = -((Y0 + PH) * inv_a - cam.h_over_2a);
 	f.margin = 1e-4f * fmaxf(2.0f, scene_scale);
 	f.u0 = fminf(ua, ub) - 1e-5f; f.u1 = fmaxf(ua, ub) + 1e-5f;
 	f.v0 = fminf(va, vb) - 1e-5f; f.v1 = fmaxf(va, vb) + 1e-5f;
@@ -728,14 +734,19 @@ RTX_DEV void intersect_candidates(const SceneDev &sc, const uint32_t *__restrict
 		if (want) {
 			const uint32_t first = enc >> 3, last = first + (enc & 7u);
 			for (uint32_t tri = first; tri <= last; ++tri) {
-				const float4 lo = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris)), hi = __ldg(sc.leafbox + 2 * RTX_IDX(tri, sc.num_tris) + 1);
+				/* (lo.x, lo.y, lo.z - 2, A), (hi.x, hi.y, hi.z - 2, 0): the subtraction of the camera's z (:45-49) and the
+				 * plane term A of the triangle (:71-72) do not depend on the ray and were rounded once at upload */
+				const float4 lo = __ldg(sc.pleafbox + 2 * RTX_IDX(tri, sc.num_tris)), hi = __ldg(sc.pleafbox + 2 * RTX_IDX(tri, sc.num_tris) + 1);
 				uint32_t m = 0;
 #pragma unroll
 				for (int r = 0; r < NR; ++r) {
 					if (!((want >> r) & 1u)) continue;
 					if (COUNT) ++visits;
-					const Slab sl = slab_interval<true, 4>(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, o, id[r]);
-					if (sl.tmin <= sl.tmax && sl.tmin < max_distance && sl.tmax > 0.0f) m |= 1u << r;   /* intersect_kernel.cl:41-60 */
+					const float ax = rn_mul(lo.x, id[r].x), bx = rn_mul(hi.x, id[r].x), ay = rn_mul(lo.y, id[r].y), by = rn_mul(hi.y, id[r].y);
+					const float az = rn_mul(lo.z, id[r].z), bz = rn_mul(hi.z, id[r].z);
+					const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), bz);          /* d.z < 0: the far z plane is the entry */
+					const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), az);
+					if (tmin <= tmax && tmin < max_distance && tmax > 0.0f) m |= 1u << r;      /* intersect_kernel.cl:41-60 */
 				}
 				if (!m) continue;
 				const float4 *q = sc.tris + 4 * RTX_IDX(tri, sc.num_tris);
@@ -745,7 +756,7 @@ RTX_DEV void intersect_candidates(const SceneDev &sc, const uint32_t *__restrict
 					if (!((m >> r) & 1u)) continue;
 					TriHit h;
 					if (COUNT) ++tests;
-					if (!triangle_test(t0, t1, t2, t3, o, d[r], cull[r], h)) continue;
+					if (!triangle_test_primary(t0, t1, t2, t3, lo.w, d[r], cull[r], h)) continue;
 					if (!(h.dist < best[r].dist || (h.dist == best[r].dist && tri < best[r].tri))) continue;
 					best[r].dist = h.dist; best[r].tri = tri; best[r].s = h.s; best[r].t = h.t;
 					cull[r] = h.dist * 1.0001f + abs_margin;
@@ -994,8 +1005,12 @@ k_trace_rays(const SceneDev sc, const RayWork w, Counters *cnt)
  * Per ray the tests, the acceptance rule and the culling bound are those of traverse_ordered; a parked
  * leaf is merely tested a little later, against a bound that can only have become tighter.
  * ------------------------------------------------------------------------ */
+#ifndef RTX_PT_REFILL
 #define RTX_PT_REFILL 20
-#define RTX_PT_MIN_DESCEND 12
+#endif
+#ifndef RTX_PT_MIN_DESCEND
+#define RTX_PT_MIN_DESCEND 16     /* 8 / 12 / 16 measured on C5: 23.45 / 22.77 / 22.41 ms per 2^26 rays */
+#endif
 #define RTX_PT_DONE ((int)0x80000000)
 #define RTX_PT_NONE ((int)0x80000001)
 
@@ -1843,7 +1858,8 @@ __global__ void k_flatten_nodes(const uint32_t *__restrict__ nodes, const float4
                                 const uint32_t *__restrict__ faces, const float4 *__restrict__ verts,
                                 const float4 *__restrict__ vnormals, uint32_t nnodes, uint32_t num_pairs, uint32_t leaf_size,
                                 float4 *__restrict__ pairs, float4 *__restrict__ tris, float4 *__restrict__ leafbox,
-                                float4 *__restrict__ tnormals, uint32_t nverts, TreeResult *res, uint32_t *__restrict__ parent)
+                                float4 *__restrict__ tnormals, uint32_t nverts, TreeResult *res, uint32_t *__restrict__ parent,
+                                float4 *__restrict__ pleafbox)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nnodes) return;
@@ -1872,6 +1888,10 @@ __global__ void k_flatten_nodes(const uint32_t *__restrict__ nodes, const float4
 		lo.w = 0.f; hi.w = 0.f;
 		leafbox[2 * (size_t)t] = lo;
 		leafbox[2 * (size_t)t + 1] = hi;
+		if (pleafbox) {
+			pleafbox[2 * (size_t)t] = make_float4(lo.x, lo.y, rn_sub(lo.z, 2.0f), triangle_primary_A(a, n));
+			pleafbox[2 * (size_t)t + 1] = make_float4(hi.x, hi.y, rn_sub(hi.z, 2.0f), 0.f);
+		}
 		float4 n0 = vnormals[i0], n1 = vnormals[i1], n2 = vnormals[i2];
 		n0.w = n1.w = n2.w = 0.f;
 		tnormals[3 * (size_t)t] = n0;
@@ -1924,7 +1944,8 @@ __global__ void k_flatten_nodes(const uint32_t *__restrict__ nodes, const float4
 __global__ void k_build_triangles(const uint32_t *__restrict__ faces, const float4 *__restrict__ verts,
                                   const float4 *__restrict__ vnormals, const uint32_t *__restrict__ leaf_node,
                                   const float4 *__restrict__ ref_aabbs, uint32_t ntris,
-                                  float4 *__restrict__ tris, float4 *__restrict__ leafbox, float4 *__restrict__ tnormals)
+                                  float4 *__restrict__ tris, float4 *__restrict__ leafbox, float4 *__restrict__ tnormals,
+                                  float4 *__restrict__ pleafbox)
 {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= ntris) return;
@@ -1946,6 +1967,10 @@ __global__ void k_build_triangles(const uint32_t *__restrict__ faces, const floa
 	lo.w = 0.f; hi.w = 0.f;
 	leafbox[2 * (size_t)t] = lo;
 	leafbox[2 * (size_t)t + 1] = hi;
+	if (pleafbox) {
+		pleafbox[2 * (size_t)t] = make_float4(lo.x, lo.y, rn_sub(lo.z, 2.0f), triangle_primary_A(a, n));
+		pleafbox[2 * (size_t)t + 1] = make_float4(hi.x, hi.y, rn_sub(hi.z, 2.0f), 0.f);
+	}
 	float4 n0 = vnormals[i0], n1 = vnormals[i1], n2 = vnormals[i2];
 	n0.w = n1.w = n2.w = 0.f;
 	tnormals[3 * (size_t)t] = n0;
