@@ -268,6 +268,14 @@ int rtx_peer_close(rtx_ctx *ctx, void *device_ptr);
 int rtx_peer_free(rtx_ctx *ctx, void *device_ptr);
 int rtx_copy_to_host(rtx_ctx *ctx, void *host_dst, const void *device_src, size_t bytes);   /* blocking, after all queued work */
 
+/* Ordering the ranks of the peer-memory paths without a collective: monotonic 32-bit frame counters in a (zeroed)
+ * rtx_peer_alloc buffer every rank maps.  rtx_peer_signal_async stores `value` behind everything queued before it on
+ * `stream` (system-scope release); rtx_peer_wait_async holds `stream` until flags[0..count) have all reached `value`.
+ * A wait gives up after ~2 s of device time and sets *timed_out (device memory, e.g. a word of the same buffer) to 1
+ * instead of hanging.  The waiter and the signaller must run on different GPUs. */
+int rtx_peer_signal_async(rtx_ctx *ctx, void *flag, uint32_t value, void *stream);
+int rtx_peer_wait_async(rtx_ctx *ctx, const void *flags, uint32_t count, uint32_t value, void *timed_out, void *stream);
+
 /* Page-lock and device-map caller-owned host memory (a shared mapping several rank processes opened). */
 int rtx_host_register(void *p, size_t bytes, void **device_alias);
 int rtx_host_unregister(void *p);

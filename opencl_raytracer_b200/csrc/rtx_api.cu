@@ -1537,6 +1537,30 @@ int rtx_peer_free(rtx_ctx *c, void *device_ptr)
 	return RTX_OK;
 }
 
+/* Frame counters in peer memory instead of a collective (k_peer_signal / k_peer_wait): `flag` / `flags` point into a
+ * buffer of rtx_peer_alloc (zero-initialised) mapped by the ranks.  Waits give up after ~2 s of device time and set
+ * flags[count_or_64 ...]: see rtx_peer_wait_async. */
+int rtx_peer_signal_async(rtx_ctx *c, void *flag, uint32_t value, void *stream)
+{
+	if (!c || !flag) return fail(c, RTX_ERR_ARG, "null argument");
+	CU(c, cudaSetDevice(c->device));
+	k_peer_signal<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned int *>(flag), value);
+	CU(c, cudaGetLastError());
+	return RTX_OK;
+}
+
+/* Wait until flags[0 .. count) have all reached `value` (monotonic counters, wrap-safe).  `timed_out` (one word, may
+ * live in the same buffer) is set to 1 if a counter did not arrive within ~2 s: the stream goes on, nothing hangs. */
+int rtx_peer_wait_async(rtx_ctx *c, const void *flags, uint32_t count, uint32_t value, void *timed_out, void *stream)
+{
+	if (!c || !flags || !timed_out || count == 0 || count > 1024) return fail(c, RTX_ERR_ARG, "bad argument");
+	CU(c, cudaSetDevice(c->device));
+	k_peer_wait<<<1, (count + 31) / 32 * 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned int *>(flags), count, value,
+	                                                                               static_cast<unsigned int *>(timed_out), 4000000000ll);
+	CU(c, cudaGetLastError());
+	return RTX_OK;
+}
+
 /* Page-lock caller-owned host memory (e.g. a shared mapping that several rank processes opened) and map it into the
  * device's address space; *device_alias is what kernels of this process may write (== p under unified addressing). */
 int rtx_host_register(void *p, size_t bytes, void **device_alias)

@@ -504,7 +504,7 @@ done:
  * ------------------------------------------------------------------------ */
 #define RTX_QCAP 128     /* breadth-first queue of node pairs, per warp */
 #define RTX_CCAP 192     /* candidate leaves per 32x32-pixel tile */
-#define RTX_LIST_STRIDE (2 * RTX_CCAP + 4)   /* words per tile list: [count, pad x3, enc[CCAP], key[CCAP]] */
+#define RTX_LIST_STRIDE (2 * RTX_CCAP + 4)   /* words per tile list: [count, tile x, tile y, pad, enc[CCAP], key[CCAP]] (16-byte aligned) */
 
 struct Frustum { float u0, u1, v0, v1, margin; };   /* ray = (0,0,2) + s * (u, v, -1), s >= 0 */
 
@@ -640,6 +640,7 @@ k_frustum_collect(const SceneDev sc, const Work w, const uint32_t *__restrict__ 
 	const uint32_t tx = tile % w.tiles_x, ty = tile / w.tiles_x;
 	const Frustum f = make_frustum(w.cam, (float)(tx * RTX_TILE), (float)(ty * RTX_TILE), (float)RTX_TILE, (float)RTX_TILE, sc.scene_scale);
 	uint32_t *out = lists + (size_t)ltile * RTX_LIST_STRIDE;
+	if (lane == 0) { out[1] = tx; out[2] = ty; }        /* the list kernel reads them with the count: no division per packet */
 	const uint32_t stiles_x = (w.tiles_x + RTX_SUPER - 1) / RTX_SUPER;
 	const uint32_t *sl = slists ? slists + ((size_t)(ty / RTX_SUPER) * stiles_x + tx / RTX_SUPER) * RTX_SLIST_STRIDE : nullptr;
 	const int n = sl ? (int)__ldg(sl) : -1;             /* no super-tile pass (few tiles): walk the tree per tile */
@@ -798,12 +799,18 @@ k_render_packet(const SceneDev sc, const Work w, Counters *cnt)
 		if (unit >= w.tile_count * UPT) break;
 		const uint32_t ltile = w.tile_begin + unit / UPT, sub = unit % UPT;
 		int nlist = -1;
+		uint32_t tx, ty;
 		if (MODE != 0) {
-			nlist = (int)__ldg(w.lists + (size_t)ltile * RTX_LIST_STRIDE);
+			const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(w.lists + (size_t)ltile * RTX_LIST_STRIDE));   /* count, tile x, tile y */
+			nlist = (int)hdr.x;
 			if ((MODE == 1) == (nlist < 0)) continue;       /* MODE 1 takes listed tiles, MODE 2 the overflowed ones */
+			tx = hdr.y;
+			ty = hdr.z;
+		} else {
+			const uint32_t tile = ltile * w.world + w.rank;
+			tx = tile % w.tiles_x;
+			ty = tile / w.tiles_x;
 		}
-		const uint32_t tile = ltile * w.world + w.rank;
-		const uint32_t tx = tile % w.tiles_x, ty = tile / w.tiles_x;
 		const uint32_t px0 = (sub % UX) * (8 * RX) + (lane & 7u) * RX, py0 = (sub / UX) * (4 * RY) + (lane >> 3) * RY;
 		f3 d[NR];
 		HitRec best[NR];
@@ -1602,6 +1609,35 @@ k_store_tiles(const float *__restrict__ tiles, uint32_t tile_begin, uint32_t loc
 			if (x0 + px < W && y0 + py < H) image[(size_t)(y0 + py) * W + x0 + px] = src[i];
 		}
 	}
+}
+
+/* --------------------------------------------------------------------------
+ * Ordering the ranks of the peer-memory paths without a collective: a monotonic frame counter per rank in rank 0's
+ * memory.  A rank signals after its store kernel (k_peer_signal, next in its stream: the stores of the finished kernel
+ * have been performed, the fence orders the flag behind them); rank 0 waits for every counter before it reads the frame
+ * (k_peer_wait); a rank waits for rank 0's "consumed" counter before it overwrites a buffer.  Every wait gives up after
+ * max_cycles and records that in *timed_out instead of hanging the GPU.  Waiter and signaller run on DIFFERENT GPUs.
+ * ------------------------------------------------------------------------ */
+__global__ void k_peer_signal(unsigned int *flag, unsigned int value)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	__threadfence_system();
+	asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(value) : "memory");
+}
+
+__global__ void k_peer_wait(const unsigned int *flags, unsigned int count, unsigned int value, unsigned int *timed_out, long long max_cycles)
+{
+	const unsigned int t = threadIdx.x;
+	if (blockIdx.x != 0 || t >= count) return;
+	const long long t0 = clock64();
+	for (;;) {
+		unsigned int v;
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + t) : "memory");
+		if ((int)(v - value) >= 0) break;
+		if (clock64() - t0 > max_cycles) { atomicExch(timed_out, 1u); break; }
+		__nanosleep(200);
+	}
+	__threadfence_system();
 }
 
 /* rank-major gathered compact u8 tiles -> row-major width x height byte image (rank 0).  One thread per output row of

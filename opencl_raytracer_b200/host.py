@@ -39,7 +39,7 @@ ABI_SYMBOLS = (
     "rtx_probe_bandwidth", "rtx_resize_u8_async", "rtx_deinterleave_u8_async", "rtx_render_download",
     "rtx_upload_mesh", "rtx_download_tree", "rtx_build_stats", "rtx_download_normals",
     "rtx_resize_u8_to_async", "rtx_store_tiles_async", "rtx_adopt_u8", "rtx_peer_alloc", "rtx_peer_open", "rtx_peer_close",
-    "rtx_peer_free", "rtx_host_register", "rtx_host_unregister", "rtx_phase_ms", "rtx_copy_to_host", "rtx_bind_output_image", "rtx_render_store", "rtx_render_store_async", "rtx_debug_bounds",
+    "rtx_peer_free", "rtx_host_register", "rtx_host_unregister", "rtx_phase_ms", "rtx_copy_to_host", "rtx_bind_output_image", "rtx_render_store", "rtx_render_store_async", "rtx_debug_bounds", "rtx_peer_signal_async", "rtx_peer_wait_async",
 )
 
 
@@ -179,6 +179,10 @@ def load_library():
     lib.rtx_render_store_async.argtypes = [vp, vp, vp]
     lib.rtx_debug_bounds.restype = C.c_int
     lib.rtx_debug_bounds.argtypes = [vp, C.POINTER(C.c_uint * 4)]
+    lib.rtx_peer_signal_async.restype = C.c_int
+    lib.rtx_peer_signal_async.argtypes = [vp, vp, C.c_uint32, vp]
+    lib.rtx_peer_wait_async.restype = C.c_int
+    lib.rtx_peer_wait_async.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp]
     lib.rtx_copy_to_host.restype = C.c_int
     lib.rtx_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
     lib.rtx_phase_ms.restype = C.c_int
@@ -480,6 +484,12 @@ class CudaHost:
         p = C.c_void_p()
         self._ck(self._lib.rtx_peer_open(self._ctx, C.create_string_buffer(handle, 64), C.byref(p)))
         return p.value
+
+    def peer_signal_async(self, flag: int, value: int, stream: int = 0):
+        self._ck(self._lib.rtx_peer_signal_async(self._ctx, C.c_void_p(flag), value & 0xffffffff, C.c_void_p(stream)))
+
+    def peer_wait_async(self, flags: int, count: int, value: int, timed_out: int, stream: int = 0):
+        self._ck(self._lib.rtx_peer_wait_async(self._ctx, C.c_void_p(flags), count, value & 0xffffffff, C.c_void_p(timed_out), C.c_void_p(stream)))
 
     def peer_close(self, ptr: int):
         self._ck(self._lib.rtx_peer_close(self._ctx, C.c_void_p(ptr)))

@@ -91,16 +91,21 @@ class TiledRenderer:
       "u8"         every rank applies RayTracer::resize to its own tiles, ONE NCCL gather of the bytes + de-interleave
                    ((n*n*4)x less traffic into rank 0; needs sqrt(nSuperSamples) to divide 32)
       "p2p_u8"     no collective on the data path: every rank's resize kernel stores its bytes straight into its slot of
-                   a buffer in rank 0's memory through NVLink peer memory (CUDA IPC mapping, set up once); a one-element
-                   all-reduce on the same stream completes on rank 0 only when every rank's store kernel has finished;
-                   rank 0 de-interleaves.  Two buffers alternate, so rank 0 may read frame k while k+1 is written.
+                   a buffer in rank 0's memory through NVLink peer memory (CUDA IPC mapping, set up once); the ranks are
+                   ordered by frame counters in that memory (``sync``, below); rank 0 de-interleaves.  Two buffers
+                   alternate, so rank 0 may read frame k while k+1 is written.
       "p2p_float"  the float image: in every rank's traversal kernel the warp that finishes a tile sends it to its place in
                    rank 0's row-major image (rtx_render_store_async on the peer mapping), so the transfer overlaps the
-                   tracing; same rendezvous.  (Writing each pixel remotely as it is shaded, rtx_bind_output_image, moves
+                   tracing; same ordering.  (Writing each pixel remotely as it is shaded, rtx_bind_output_image, moves
                    8-byte pieces over NVLink: 1.68 ms against 1.03 ms of tracing at 4 GPUs.)
     """
 
-    def __init__(self, rt, scene, rank: int, world: int, device: int, jitter_seed: int = 0, gather: str = "float"):
+    def __init__(self, rt, scene, rank: int, world: int, device: int, jitter_seed: int = 0, gather: str = "float", sync: str = "flags"):
+        """sync (p2p modes): how the ranks are ordered once their stores are queued --
+        "flags"      frame counters in rank 0's memory (rtx_peer_signal_async / rtx_peer_wait_async): a rank raises its counter
+                     behind its store kernel, rank 0 waits for all of them, and a rank waits for rank 0's "consumed" counter
+                     before it overwrites a buffer.  No collective at all in the frame; waits time out instead of hanging.
+        "allreduce"  a one-element NCCL all-reduce on the same stream."""
         import torch
         from . import host
         self.torch = torch
@@ -124,6 +129,8 @@ class TiledRenderer:
         self.timing = False          # record torch events around the multi-GPU phases (phase_ms)
         self._ev = None
         self.peer = None             # p2p modes: the two final images in rank 0's memory, as seen from this rank
+        self.sync = sync
+        self.flags = None            # p2p modes, sync="flags": 128 counters in rank 0's memory ([r] arrived, [64] consumed, [65] timed out)
         if gather == "u8" and world > 1:
             m = TILE // rt.n
             self.local_u8 = torch.zeros(tile_counts(rt.totalWidth, rt.totalHeight, world)[2] * m * m, dtype=torch.uint8, device=self.dev)
@@ -136,22 +143,24 @@ class TiledRenderer:
             box, err = [None], None
             if rank == 0:
                 try:
-                    owned = [self.host.peer_alloc(nbytes) for _ in range(2)]
+                    owned = [self.host.peer_alloc(nbytes) for _ in range(2)] + [self.host.peer_alloc(512)]
                     box = [[h for _, h in owned]]
-                    self.peer = [p for p, _ in owned]
+                    self.peer = [p for p, _ in owned[:2]]
+                    self.flags = owned[2][0]
                 except host.RtxError as e:
                     err = str(e)
             dist.broadcast_object_list(box, src=0)
             if rank != 0 and box[0] is not None:
                 try:
-                    self.peer = [self.host.peer_open(h) for h in box[0]]
+                    opened = [self.host.peer_open(h) for h in box[0]]
+                    self.peer, self.flags = opened[:2], opened[2]
                 except host.RtxError as e:
                     err = str(e)
             ok = torch.tensor([0 if (err or box[0] is None) else 1], dtype=torch.int32, device=self.dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 0:
                 if self.peer and rank == 0:
-                    for p in self.peer:
+                    for p in self.peer + [self.flags]:
                         self.host.peer_free(p)
                 self.peer = None
                 self.host.close()
@@ -169,6 +178,10 @@ class TiledRenderer:
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         if self.timing:
             self._ev = []
+        flags_sync = self.peer is not None and self.sync == "flags"
+        if flags_sync and self.rank != 0 and self.frame >= 2:
+            # this frame's buffer was last used by frame - 2: rank 0 must have consumed that one
+            self.host.peer_wait_async(self.flags + 4 * 64, 1, self.frame - 1, self.flags + 4 * 65, stream)
         if self.gather == "p2p_float":
             # the traversal kernel sends every finished tile to its place in rank 0's image (128-byte rows over NVLink)
             self.host.render_store_async(self.peer[self.frame & 1], stream)
@@ -206,10 +219,19 @@ class TiledRenderer:
                 self.host.resize_u8_async(target + self.rank * self.u8_per_rank, self.u8_per_rank, stream)
                 self.kernel_launches += 1
             self._mark("gather")
-            dist.all_reduce(self.flag)                            # rendezvous: every rank's stores have landed
+            if flags_sync:
+                self.host.peer_signal_async(self.flags + 4 * self.rank, self.frame + 1, stream)     # behind this rank's stores
+                if self.rank == 0:
+                    self.host.peer_wait_async(self.flags, self.world, self.frame + 1, self.flags + 4 * 65, stream)
+                self.kernel_launches += 1 if self.rank else 2
+            else:
+                dist.all_reduce(self.flag)                        # rendezvous: every rank's stores have landed
             if self.rank == 0 and self.gather == "p2p_u8":
                 self._mark("deinterleave")
                 self.host.deinterleave_u8_async(target, self.world, stream)
+                self.kernel_launches += 1
+            if flags_sync and self.rank == 0:
+                self.host.peer_signal_async(self.flags + 4 * 64, self.frame + 1, stream)            # frame consumed
                 self.kernel_launches += 1
             self.last_target = target
         self._mark("end")
@@ -224,9 +246,16 @@ class TiledRenderer:
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
         return out
 
+    def _check_flags(self):
+        if self.peer is not None and self.sync == "flags":
+            words = self.host.copy_to_host(np.zeros(128, np.uint32), self.flags)
+            if words[65]:
+                raise RuntimeError("a rank did not arrive within the time-out of the peer-memory frame counters: %s" % words[:self.world])
+
     def download(self):
         assert self.rank == 0
         self.torch.cuda.synchronize(self.dev)
+        self._check_flags()
         if self.gather == "p2p_float":
             return self.host.copy_to_host(np.empty((self.rt.totalHeight, self.rt.totalWidth), np.float32), self.last_target)
         return self.host.download()
@@ -234,6 +263,7 @@ class TiledRenderer:
     def download_u8(self):
         assert self.rank == 0
         self.torch.cuda.synchronize(self.dev)
+        self._check_flags()
         return self.host.download_u8()
 
     def close(self):
@@ -243,10 +273,10 @@ class TiledRenderer:
                 import torch.distributed as dist
                 dist.barrier()                        # nobody unmaps or frees while a peer may still store
             if self.rank == 0:
-                for p in self.peer:
+                for p in self.peer + [self.flags]:
                     self.host.peer_free(p)
             else:
-                for p in self.peer:
+                for p in self.peer + [self.flags]:
                     self.host.peer_close(p)
             self.peer = None
         self.host.close()

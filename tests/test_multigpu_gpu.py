@@ -35,13 +35,13 @@ def _worker(rank, world, port, out_dir):
         v, f = scenes.sibenik_standin(detail=0.35)
         sc = scene.scene_from_mesh(v, f)
         rt = host.RayTracer(host.Options(width=416, height=232, nSuperSamples=16))     # 1664 x 928 rays: 52 x 29 tiles
-        for mode in ("float", "u8", "p2p_u8", "p2p_float"):
-            r = multigpu.TiledRenderer(rt, sc, rank, world, rank, gather=mode)
-            for _ in range(3):                      # both of the alternating p2p images get used
+        for mode, sync in (("float", ""), ("u8", ""), ("p2p_u8", "flags"), ("p2p_float", "flags"), ("p2p_u8", "allreduce"), ("p2p_float", "allreduce")):
+            r = multigpu.TiledRenderer(rt, sc, rank, world, rank, gather=mode, sync=sync or "flags")
+            for _ in range(5):                      # both of the alternating p2p images get used, ranks run ahead of each other
                 r.render_frame()
             if rank == 0:
                 img = r.download_u8() if mode.endswith("u8") else r.download()
-                np.save(os.path.join(out_dir, mode + ".npy"), img)
+                np.save(os.path.join(out_dir, mode + ("_" + sync if sync == "allreduce" else "") + ".npy"), img)
             torch.cuda.synchronize()
             dist.barrier()
             r.close()
@@ -85,7 +85,7 @@ def test_two_gpus_every_gather_mode(tmp_path, po):
         want_f, want_b = h.download(), h.download_u8()
     ref = po.render(sc, rt.totalWidth, rt.totalHeight, 1.0, True, want_ids=False).image
     assert np.array_equal(want_f, ref)
-    for mode in ("float", "p2p_float", "shared_host"):
+    for mode in ("float", "p2p_float", "p2p_float_allreduce", "shared_host"):
         assert np.array_equal(np.load(str(tmp_path / (mode + ".npy"))), want_f), mode
-    for mode in ("u8", "p2p_u8"):
+    for mode in ("u8", "p2p_u8", "p2p_u8_allreduce"):
         assert np.array_equal(np.load(str(tmp_path / (mode + ".npy"))), want_b), mode
