@@ -57,10 +57,10 @@ CPU_ROW_STEP = 16      # both CPU legs time every 16th row of the frame (rows 8,
 def make_config(desc, scene_name, ntris, tw, th, world, gather):
     """The `config` object, identical in the GPU arm and in --impl reference (the driver compares the two)."""
     nrows = len(range(CPU_ROW_STEP // 2, th, CPU_ROW_STEP))
-    how = {"auto": "every rank's resize kernel stores its bytes into rank 0's memory over NVLink, ordered by frame counters in that memory "
+    how = {"auto": "every rank's resize kernel stores its bytes into rank 0's memory over NVLink, ordered by a one-element all-reduce "
                    "(one NCCL gather of the bytes + de-interleave where the GPUs cannot map each other's memory)",
-           "p2p_u8": "every rank's resize kernel stores its bytes into rank 0's memory over NVLink, ordered by frame counters in that memory",
-           "p2p_float": "every rank's traversal kernel sends finished float tiles into rank 0's image over NVLink, ordered by frame counters",
+           "p2p_u8": "every rank's resize kernel stores its bytes into rank 0's memory over NVLink, ordered by a one-element all-reduce",
+           "p2p_float": "every rank's traversal kernel sends finished float tiles into rank 0's image over NVLink, ordered by a one-element all-reduce",
            "u8": "1 NCCL gather of the bytes + de-interleave", "float": "1 NCCL gather of the float tiles + de-interleave"}[gather]
     return {"workload": desc, "scene": scene_name, "triangles": int(ntris), "rays_per_step": int(tw * th),
             "parallelism": "interleaved 32x32 tiles over %d GPU(s), scene replicated, frame assembled on rank 0" % world,
@@ -645,7 +645,7 @@ def main():
     phases_ms = {"max_over_ranks": {k: float(v) for k, v in zip(phase_names, pt.cpu().numpy())},
                  "mean_over_ranks": {k: float(v) for k, v in zip(phase_names, pt_mean.cpu().numpy())},
                  "how": "CUDA events around each launch group of %d extra frames (rtx_phase_ms + torch events in multigpu.TiledRenderer); "
-                        "'gather' = the NCCL gather (p2p modes: the frame-counter signal + rank 0's wait for every rank), 'resize' includes the peer stores in p2p_u8" % nph}
+                        "'gather' = the NCCL gather (p2p modes: the one-element all-reduce, i.e. rank 0 waiting for the slowest rank), 'resize' includes the peer stores in p2p_u8" % nph}
 
     # parity spot check inside the bench (rank 0): sampled rows of the gathered frame == oracle
     parity = None
@@ -673,8 +673,8 @@ def main():
     other = None
     if world > 1:
         other = []
-        for alt, sync in (("u8", "flags"), ("float", "flags"), ("p2p_u8", "flags"), ("p2p_float", "flags"), ("p2p_u8", "allreduce")):
-            if alt == args.gather and sync == "flags":
+        for alt, sync in (("u8", "allreduce"), ("float", "allreduce"), ("p2p_u8", "allreduce"), ("p2p_float", "allreduce"), ("p2p_u8", "flags")):
+            if alt == args.gather and sync == "allreduce":
                 continue
             try:
                 r2 = multigpu.TiledRenderer(rt, sc, rank, world, local_rank, gather=alt, sync=sync)
@@ -697,7 +697,7 @@ def main():
             tms = torch.tensor(ts, dtype=torch.float64, device=dev)
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
             ms = float(tms.mean().item())
-            other.append({"gather": alt + (" (ranks ordered by a one-element all-reduce)" if sync == "allreduce" else ""),
+            other.append({"gather": alt + (" (ranks ordered by frame counters in peer memory instead of the all-reduce)" if sync == "flags" else ""),
                           "ms_per_step": ms, "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s"})
             barrier()
             r2.close()
