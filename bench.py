@@ -1,26 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- Mrays/s closest-hit on the sibenik stand-in at 4K (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1|c4|c5] [--gather MODE]
 
 Workload (default, all N): config C3 -- sibenik stand-in (75 256 triangles), `render -a 0 -w 3840 -h 2160
 -s 16` => 15360 x 8640 = 132 710 400 primary rays per frame on the reference's regular 4x4 sample grid,
-image tile-partitioned over the N GPUs (strong scaling), one NCCL gather to rank 0 per frame.
-A "step" = one frame: traversal kernel on every rank (+ gather + de-interleave when N > 1).
+image tile-partitioned over the N GPUs (strong scaling).  A "step" = one frame: the traversal kernels on every rank +
+RayTracer::resize on the device -> the byte image on rank 0 (N > 1: every rank's resize kernel stores its bytes into
+rank 0's memory over NVLink peer memory, `--gather auto`; the NCCL-gather modes are timed beside it in `other_gather`).
 
   value      rays of the frame / device time of the step (CUDA events on the launching stream, max over
-             ranks), scene resident in HBM.
-  e2e        the same frame through the reference's five calls on HOST buffers (rtx_upload of the five
-             reference arrays -> rtx_render -> rtx_download of the float image), copies inside the timed
-             region; e2e_u8 is the opt-in variant that resizes on the device and downloads bytes.
-  roofline   algorithmic bytes (B = 32 V + 48 T + 48 h + 4 per ray, V/T/h counted by the oracle
-             under the reference's exhaustive walk) x rays / kernel time, against the measured HBM peak.
-             The scene (11 MB) lives in L2/L1, so `frac` may exceed 1: the cache-level numbers that
-             actually bound the kernel are in roofline.l2 (measured L2 peak from rtx_probe_bandwidth).
-  cpu_baseline  the reference's own kernel text (oracle/_ref) -- or the C port when it is absent -- on the
-             box's host cores, on a bounded row sample of the same frame.
+             ranks), scene resident in HBM, L2 flushed between steps.
+  e2e        the same frame through the C ABI on HOST buffers, copies inside the timed region.  N = 1: rtx_upload of the
+             five reference arrays + rtx_render_download of the float image (tracing and copy pipelined over bands).
+             N > 1: every rank rtx_upload + rtx_render_store into ONE page-locked host image all rank processes map, so
+             each rank's tiles leave over its own PCIe link.  e2e_u8: device resize + byte download.
+  roofline   top level = the level that binds, instruction issue: warp instructions of the dominant kernel (ncu capture of
+             THIS build, profiles/traffic.json stamped with the kernel sources' sha256; null when stale or N > 1) over its
+             measured time, against SMs x 4 schedulers x the sampled SM clock.  Beside it: the DRAM / L2 / L1 bytes of the
+             same capture (hbm_actual, memory_levels) and SURVEY 8d's algorithmic-bytes figure (algorithmic_vs_hbm:
+             B = 32 V + 48 T + 48 h + 4 per ray under the reference's exhaustive walk, > 1 because that work is not done).
+  cpu_baseline  the reference's own kernel text (oracle/_ref) -- or the C port when it is absent -- on the box's host
+             cores, on a fixed row sample of the same frame (every 16th row).
+  phases_ms  device time per launch group of a frame; extras (N = 1): configs C4 and C5, an irregular interior, other paths.
 
---impl reference runs only that CPU arm (rank 0) with the same JSON shape.
+--impl reference runs only the CPU arm (rank 0) with the same JSON shape and the same `config`; it loads nothing of this
+repo's product (scene from the reference's own mesh.cc + bvh.cc in oracle/_ref).
 """
 from __future__ import annotations
 
