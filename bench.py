@@ -878,27 +878,31 @@ def main():
         l2_peak = r.host.probe_bandwidth(0, 32 << 20, 20)
         # profiler-only quantities (instruction count, bytes per memory level) come from a capture of THIS build at
         # N = 1, or not at all: a stale or other-N capture is never scaled into the line
-        prof, prof_src = load_profile(args.workload) if world == 1 else (None, "captures are per N; only the 1-GPU launch is profiled")
+        # ... at N > 1 a capture of ONE RANK'S share of the frame (rank 0 of N rendered on one GPU, tools/rank_timing.py
+        # under ncu: the very kernel launch a rank of the N-GPU run executes), key "<workload>@N"
+        prof, prof_src = load_profile(args.workload if world == 1 else "%s@%d" % (args.workload, world))
         sms = host.device_info(local_rank).sm_count
-        share = (prof or {}).get("share_of_kernel_ms_pct", 100.0) / 100.0      # dominant kernel's share of the event pair
+        ph = phases_ms["mean_over_ranks"]
+        render_ph = sum(ph[k] for k in ("tables", "collect_super", "collect", "traversal", "overflow"))
+        share = ph["traversal"] / render_ph if render_ph > 0 else 1.0          # dominant kernel's share of the event pair, measured in this run
         issue = hbm_actual = levels = None
         traffic = None
         if prof:
             dom_s = kernel_s * share
             traffic = (prof.get("dram_bytes_read") or 0) + (prof.get("dram_bytes_write") or 0)
             hbm_actual = {"bytes_per_launch": traffic, "GBps": traffic / dom_s / 1e9, "frac_of_peak": traffic / dom_s / 1e9 / peak,
-                          "compulsory_bytes": 4 * rays, "note": "compulsory HBM traffic of this workload is the 4 B/ray image write"}
+                          "compulsory_bytes": 4 * rays // world, "note": "per rank; compulsory HBM traffic of this workload is the 4 B/ray image write"}
             if prof.get("warp_instructions") and clocks.get("sm_mhz"):
                 ach = prof["warp_instructions"] / dom_s / 1e9
                 pk = sms * 4 * clocks["sm_mhz"] * 1e6 / 1e9
                 issue = {"achieved": ach, "peak": pk, "frac": ach / pk,
                          "warp_instructions_per_launch": prof["warp_instructions"],
-                         "thread_instructions_per_ray": (prof["warp_instructions"] * (prof.get("avg_threads_per_instruction") or 32.0)) / rays,
+                         "thread_instructions_per_ray": (prof["warp_instructions"] * (prof.get("avg_threads_per_instruction") or 32.0)) / (rays / world),
                          "avg_threads_per_instruction": prof.get("avg_threads_per_instruction"),
                          "ncu_issue_active_pct": prof.get("issue_active_pct"), "ncu_warps_active_pct": prof.get("warps_active_pct"),
-                         "how": "warp instructions of the dominant kernel (ncu capture of this build) / (kernel_ms of this run x its %.1f %% share "
-                                "of the event pair); peak = %d SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the timed region)"
-                                % (100 * share, sms, clocks["sm_mhz"])}
+                         "how": "warp instructions of the dominant kernel%s (ncu capture of this build) / (kernel_ms of this run x its %.1f %% "
+                                "share of the event pair, from this run's phases_ms); peak = %d SMs x 4 schedulers x %.0f MHz (median SM clock "
+                                "sampled during the timed region)" % (" for one rank's share of the frame" if world > 1 else "", 100 * share, sms, clocks["sm_mhz"])}
             if prof.get("l1_load_bytes") and prof.get("l2_read_bytes_from_l1"):
                 levels = {"l1_load_GBps": prof["l1_load_bytes"] / dom_s / 1e9, "l1_hit_pct": prof.get("l1_hit_pct"),
                           "l2_read_GBps": prof["l2_read_bytes_from_l1"] / dom_s / 1e9, "l2_hit_pct": prof.get("l2_hit_pct"),

@@ -8,7 +8,8 @@ the hash and emits null instead of stale numbers when it differs.
 usage:
     python tools/make_traffic.py <workload> <report.ncu-rep> <kernel-regex> [launches.csv [companion-regex ...]]
 
-      workload     c3 | c4 | c5 ... (key in traffic.json; the entry is replaced, other entries are kept)
+      workload     c3 | c4 | c5 | c3@8 ... (key in traffic.json; the entry is replaced, other entries are kept; "@N" = one
+                   rank's share of an N-GPU frame, captured from tools/rank_timing.py N)
       report       ncu --set full capture of the bench/sweep command for that workload (one GPU)
       kernel-regex picks the dominant kernel's launch inside the report (first match is used)
       launches.csv optional `ncu --metrics gpu__time_duration.sum` launch list of the same command:
@@ -136,6 +137,8 @@ def main():
     allw["_comment"] = ("Per-launch profiler numbers of each workload's dominant kernel, written by tools/make_traffic.py from ncu --set full "
                         "captures.  Every entry is stamped with the sha256 of the kernel sources it was measured on; bench.py ignores an "
                         "entry whose stamp differs from the sources of the build it runs.")
+    if "@" in workload:
+        entry["stamp"]["what"] = "rank 0 of %s ranks, rendered on one GPU (tools/rank_timing.py): the launch a rank of the N-GPU run executes" % workload.split("@")[1]
     allw[workload] = entry
     with open(path, "w") as f:
         json.dump(allw, f, indent=1)
