@@ -622,6 +622,42 @@ def test_error_behaviour(soup_scene):
     with pytest.raises(host.RtxError) as e:
         host.CudaHost(rt, device=99)
     assert e.value.code == host.ERR_NO_DEVICE
+    # uniform sampler: the outermost ring must stay below 90 degrees (ray_count = (uint)(2 pi cos(angle) / step) is
+    # undefined for a negative cosine, intersect_kernel.cl:240): the CLI's alpha 4..90 with 32 rings reaches 91.2 degrees
+    for bad in (dict(aoNumSamples=32), dict(aoNumSamples=3, aoAlphaMin=-1), dict(aoNumSamples=3, aoAlphaMin=40, aoAlphaMax=90)):
+        with pytest.raises(host.RtxError) as e:
+            host.CudaHost(host.RayTracer(host.Options(enableAO=True, aoMethod=0, **bad)))
+        assert e.value.code == host.ERR_ARG and "ring" in str(e.value)
+    host.CudaHost(host.RayTracer(host.Options(enableAO=True, aoMethod=0, aoNumSamples=15))).close()    # 15 rings: 88 degrees, fine
+    host.CudaHost(host.RayTracer(host.Options(enableAO=True, aoMethod=1, aoNumSamples=32))).close()    # random sampler: no rings
+
+
+def test_loose_tree_takes_the_literal_walk(po, scene_mod, soup_scene):
+    """A caller-supplied tree whose parent boxes do not enclose their children breaks the one geometric property the
+    re-ordered traversals rely on (leaf box passes => every ancestor passes).  rtx_upload detects it on the device
+    (k_tree_check) and renders with the literal walk: the result is still the reference's for THOSE arrays."""
+    host = require_gpu()
+    aabbs = np.array(soup_scene.aabbs, np.float32, copy=True)
+    inner = np.flatnonzero(soup_scene.nodes > 1)
+    for i in inner[3:40:4]:                     # shrink some interior boxes to a sliver: their children stick out
+        aabbs[2 * i + 1, :3] = aabbs[2 * i, :3] + 1e-3
+    loose = scene_mod.Scene(soup_scene.faces, soup_scene.nodes, aabbs, soup_scene.vertices, soup_scene.normals)
+    rt = host.RayTracer(host.Options(width=96, height=64, nSuperSamples=4))
+    for on_device in (1, 0):
+        with host.CudaHost(rt) as h:
+            h.set_tunable(host.TUNE_FLATTEN_ON_DEVICE, on_device)
+            h.set_tunable(host.TUNE_RECORD_HITS, 1)
+            h.upload_scene(loose)
+            h()
+            assert h.stats()["kernel_variant"] == host.KERNEL_EXHAUSTIVE        # routed to the literal walk
+            ref = check_against_oracle(host, po, loose, rt, h)
+            lo, hi = loose.root_box()
+            o, d = po.gen_random_rays(7, 0, 4096, lo, hi)
+            fid, dist = h.trace_rays(o, d)
+            want = po.trace_rays(loose, o, d)
+            assert np.array_equal(fid, want.face_id) and np.array_equal(dist, want.distance)
+    good = po.render(soup_scene, rt.totalWidth, rt.totalHeight, 1.0, True)
+    assert (ref.face_id != good.face_id).any()      # the loose tree really renders differently from the proper one
 
 
 @pytest.mark.parametrize("frustum,rpt", [(-1, 1), (0, 1), (0, 0), (0, 4)])
