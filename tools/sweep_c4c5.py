@@ -44,5 +44,8 @@ for setting in sys.argv[2:]:
             if ref_sum is None:
                 ref_sum = chk
             print("%-60s %8.3f ms  %7.0f Mrays/s  %s" % (setting, best, n / best / 1e3, "same" if chk == ref_sum else "DIFFERENT RESULT"), flush=True)
+            st = h.stats()
+            if st.get("node_visits"):
+                print("    per ray: %.1f box tests, %.2f triangle tests, %.2f leaf-box tests" % (st["node_visits"] / n, st["tri_tests"] / n, st["leafbox_tests"] / n), flush=True)
     except Exception as e:          # a setting the library refuses
         print("%-60s %s" % (setting, e), flush=True)
