@@ -31,6 +31,8 @@ def parse(argv):
                     help="the O(n^2) SAH builder of bvh.cc:178-236 is not rebuilt here")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--device-build", action="store_true", help="build normals and BVH on the device (rtx_upload_mesh)")
+    ap.add_argument("--scene-cache", metavar="DIR", default=None,
+                    help="keep the prepared scene (BVH, sorted faces, normals) in DIR, keyed by the mesh file's sha256")
     return ap.parse_args(argv)
 
 
@@ -41,7 +43,7 @@ def main(argv=None) -> int:
                        aoNumSamples=a.ambient_occlusion_samples, aoMethod=0 if a.ambient_occlusion_method == "uniform" else 1,
                        aoAlphaMin=4, aoAlphaMax=90)
     t0 = time.perf_counter()
-    sc = scene.scene_from_off(a.input_mesh)
+    sc = scene.cached_scene_from_off(a.input_mesh, a.scene_cache) if a.scene_cache else scene.scene_from_off(a.input_mesh)
     t1 = time.perf_counter()
     rt = host.RayTracer(opt)
     with host.CudaHost(rt, device=a.device) as h:

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import hashlib
+import zipfile
 import os
 from dataclasses import dataclass
 
@@ -138,3 +139,82 @@ def write_off(path: str, verts3, faces) -> None:
             f.write("%.9g %.9g %.9g\n" % (v[0], v[1], v[2]))
         for t in faces:
             f.write("3 %d %d %d\n" % (t[0], t[1], t[2]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# On-disk cache of a prepared scene: the five upload arrays of render.cc:88-98 + the two index maps, keyed by
+# the input mesh.  The builder is deterministic, so a cache hit returns byte-identical arrays (the file carries their
+# sha256 and load_scene() refuses a file whose contents do not match it).
+# ---------------------------------------------------------------------------------------------------------------------
+CACHE_FORMAT = 1
+
+
+def save_scene(path: str, sc: Scene) -> None:
+    """Write a prepared scene as one .npz (written next to `path` first, then renamed: no half-written cache entries)."""
+    tmp = "%s.tmp.%d.npz" % (path, os.getpid())
+    np.savez(tmp, format=np.array([CACHE_FORMAT], np.uint32), digest=np.frombuffer(bytes.fromhex(sc.digest()), np.uint8),
+             faces=sc.faces, nodes=sc.nodes, aabbs=sc.aabbs, vertices=sc.vertices, normals=sc.normals,
+             triangles=sc.triangles if sc.triangles is not None else np.zeros(0, np.uint32),
+             orig_faces=sc.orig_faces if sc.orig_faces is not None else np.zeros(0, np.uint32),
+             name=np.frombuffer(sc.name.encode(), np.uint8))
+    os.replace(tmp, path)
+
+
+def load_scene(path: str) -> Scene:
+    """Read a scene written by save_scene; raises SceneError if the file is of another format or fails its checksum."""
+    try:
+        with np.load(path) as z:
+            if int(z["format"][0]) != CACHE_FORMAT:
+                raise SceneError(-1, "%s: cache format %d, this build reads %d" % (path, int(z["format"][0]), CACHE_FORMAT))
+            sc = Scene(faces=z["faces"], nodes=z["nodes"], aabbs=z["aabbs"], vertices=z["vertices"], normals=z["normals"],
+                       triangles=z["triangles"] if z["triangles"].size else None,
+                       orig_faces=z["orig_faces"] if z["orig_faces"].size else None, name=bytes(z["name"]).decode())
+            want = bytes(z["digest"]).hex()
+    except (OSError, KeyError, ValueError, EOFError, zipfile.BadZipFile) as e:
+        raise SceneError(-1, "%s: not a scene cache file (%s)" % (path, e))
+    if sc.digest() != want:
+        raise SceneError(-1, "%s: contents do not match the stored sha256" % path)
+    return sc
+
+
+def mesh_key(verts3, faces) -> str:
+    """Cache key of an input mesh: sha256 over its float32 vertices and uint32 faces (+ the cache format)."""
+    h = hashlib.sha256(b"rtx-scene-%d" % CACHE_FORMAT)
+    h.update(np.ascontiguousarray(verts3, np.float32).tobytes())
+    h.update(np.ascontiguousarray(faces, np.uint32).tobytes())
+    return h.hexdigest()[:32]
+
+
+def cached_scene_from_mesh(verts3, faces, cache_dir: str, nthreads: int = 0, name: str = "") -> Scene:
+    """scene_from_mesh through an on-disk cache: the 10 M-triangle scene of C4 loads in a fraction of its 2 s build.
+    A missing, unreadable or corrupt entry is rebuilt and rewritten."""
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, "scene_%s.npz" % mesh_key(verts3, faces))
+    if os.path.exists(path):
+        try:
+            sc = load_scene(path)
+            sc.name = name or sc.name
+            return sc
+        except SceneError:
+            pass
+    sc = scene_from_mesh(verts3, faces, nthreads=nthreads, name=name)
+    save_scene(path, sc)
+    return sc
+
+
+def cached_scene_from_off(path: str, cache_dir: str, nthreads: int = 0) -> Scene:
+    """scene_from_off through the same cache, keyed by the sha256 of the OFF file's bytes."""
+    os.makedirs(cache_dir, exist_ok=True)
+    h = hashlib.sha256(b"rtx-scene-off-%d" % CACHE_FORMAT)
+    with open(path, "rb") as fh:
+        for chunk in iter(lambda: fh.read(1 << 20), b""):
+            h.update(chunk)
+    entry = os.path.join(cache_dir, "scene_%s.npz" % h.hexdigest()[:32])
+    if os.path.exists(entry):
+        try:
+            return load_scene(entry)
+        except SceneError:
+            pass
+    sc = scene_from_off(path, nthreads=nthreads)
+    save_scene(entry, sc)
+    return sc
