@@ -15,8 +15,14 @@
  *   BVH::buildBVH            include/bvh.h:13         (inside both builders)
  *   leaf-order face sort     src/render.cc:88-95      rtx_scene_faces
  *
- * Only BVH::Method::CUT_LONGEST_AXIS (bvh.cc:59-94) is implemented; the
- * O(n^2) SAH split (bvh.cc:178-236) stays with the reference's own builder.
+ * Both of BVH::Method's builders: CUT_LONGEST_AXIS (bvh.cc:59-94, the CLI's
+ * default) and SURFACE_AREA_HEURISTIC (bvh.cc:178-236, `-r sah`).  The SAH
+ * split makes the reference's std::sort calls on the same sequences and keeps
+ * its float / double cost expression, so it emits the reference's tree (golden
+ * arrays from the reference builder in tests/golden/soup_sah.npz); the
+ * right-hand boxes of the sweep come from a suffix scan instead of being
+ * recomputed per cut position (min / max are exact), O(n log n) per node
+ * instead of O(n^2).
  */
 #ifndef RTX_SCENE_H
 #define RTX_SCENE_H
@@ -36,6 +42,9 @@ typedef struct rtx_scene rtx_scene;
 #define RTX_SCENE_ERR_FORMAT    3  /* "File not recognized as OFF model" / "Invalid face with != 3 vertices" */
 #define RTX_SCENE_ERR_EMPTY     4  /* no usable triangle (the reference would index nodes.at(0) of an empty tree) */
 
+#define RTX_SCENE_BVH_LONGEST_AXIS 0  /* BVH::Method::CUT_LONGEST_AXIS */
+#define RTX_SCENE_BVH_SAH          1  /* BVH::Method::SURFACE_AREA_HEURISTIC */
+
 /* Load an OFF file, compute area-weighted vertex normals, build the BVH.
  * nthreads <= 0: one builder thread per online CPU (the result does not
  * depend on the thread count). */
@@ -46,6 +55,11 @@ int rtx_scene_from_off(const char *path, int nthreads, rtx_scene **out);
  * mesh.cc:48-53). */
 int rtx_scene_from_mesh(const float *verts3, size_t nverts, const uint32_t *faces, size_t nfaces,
                         int nthreads, rtx_scene **out);
+
+/* The same with the builder named (RTX_SCENE_BVH_*), bvh.h:13 `BVH(Method)`. */
+int rtx_scene_from_off_method(const char *path, int method, int nthreads, rtx_scene **out);
+int rtx_scene_from_mesh_method(const float *verts3, size_t nverts, const uint32_t *faces, size_t nfaces, int method,
+                               int nthreads, rtx_scene **out);
 
 void rtx_scene_free(rtx_scene *scene);
 

@@ -175,6 +175,9 @@ struct Builder {
 	size_t pending = 0;
 	size_t spawn_threshold = 0;
 
+	bool sah = false;              /* BVH::Method::SURFACE_AREA_HEURISTIC (bvh.cc:178-236) instead of CUT_LONGEST_AXIS */
+	std::vector<float> suffix;     /* SAH sweep: boxes of ids[i..end), 6 floats each */
+
 	explicit Builder(rtx_scene_impl &sc) : s(sc) {}
 
 	void prepare()
@@ -191,6 +194,7 @@ struct Builder {
 			}
 		}
 		ids.resize(nt); scratch.resize(nt);
+		if (sah) suffix.resize(6 * nt);
 		for (size_t t = 0; t < nt; ++t) ids[t] = (uint32_t)t;
 		s.nodes.assign(2 * nt - 1, 0);
 		s.aabbs.assign(2 * (2 * nt - 1), V4{ 0, 0, 0, 0 });
@@ -238,6 +242,66 @@ struct Builder {
 		return nl;
 	}
 
+	/* getSurfaceArea (bvh.cc:37-42): float products and sums, doubled in double, returned as float */
+	static float surface_area(const Box &bb)
+	{
+		const float w = bb.hi[0] - bb.lo[0], h = bb.hi[1] - bb.lo[1], d = bb.hi[2] - bb.lo[2];
+		return (float)(2.0 * (double)(w * h + h * d + d * w));
+	}
+
+	/* Split ids[b, b+n) like cutFacesSAH (bvh.cc:178-236); returns the size of the left part.  The reference sorts the
+	 * node's ids by descending centroid along each axis with std::sort, sweeps every cut position (it recomputes the
+	 * right-hand box for every position: O(n^2); min / max are exact, so a suffix scan gives the same boxes), keeps the
+	 * first strictly cheaper (axis, position), sorts once more along the best axis unless that was the last one, and cuts.
+	 * The same std::sort calls on the same sequences here, so ties between equal centroids fall the same way (same
+	 * libstdc++); the cost expression keeps the reference's float / double mix. */
+	size_t split_sah(size_t b, size_t n, Box &bb)
+	{
+		bb.reset();
+		for (size_t i = b; i < b + n; ++i) bb.grow(&tlo[3 * (size_t)ids[i]], &thi[3 * (size_t)ids[i]]);
+		const float cBV2 = 1.0, cObj = 1.0;
+		const float sa_current = surface_area(bb);
+		size_t best_axis = 0, best_pos = 1;
+		float min_costs = std::numeric_limits<float>::max();
+		const auto first = ids.begin() + (std::ptrdiff_t)b, last = first + (std::ptrdiff_t)n;
+		for (size_t axis = 0; axis < 3; ++axis) {
+			const float *cen = centroid.data();
+			std::sort(first, last, [cen, axis](size_t i, size_t j) { return cen[3 * i + axis] > cen[3 * j + axis]; });
+			if (n < 3) continue;                         /* no interior cut position to evaluate (the loop at :204 is empty) */
+			/* suffix[i] = box of ids[b+i .. b+n) */
+			Box acc;
+			acc.reset();
+			for (size_t i = n; i-- > 1;) {
+				const size_t t = ids[b + i];
+				acc.grow(&tlo[3 * t], &thi[3 * t]);
+				float *o = &suffix[6 * (b + i)];
+				o[0] = acc.lo[0]; o[1] = acc.lo[1]; o[2] = acc.lo[2]; o[3] = acc.hi[0]; o[4] = acc.hi[1]; o[5] = acc.hi[2];
+			}
+			Box left;
+			left.reset();
+			left.grow(&tlo[3 * (size_t)ids[b]], &thi[3 * (size_t)ids[b]]);
+			double count_left = 1, count_right = (double)(n - 1);
+			for (size_t i = 1; i < n - 1; ++i) {
+				Box right;
+				const float *o = &suffix[6 * (b + i)];
+				right.lo[0] = o[0]; right.lo[1] = o[1]; right.lo[2] = o[2]; right.hi[0] = o[3]; right.hi[1] = o[4]; right.hi[2] = o[5];
+				const float sa_left = surface_area(left), sa_right = surface_area(right);
+				const float costs = (float)(cBV2 + (sa_left / sa_current) * count_left * cObj + (sa_right / sa_current) * count_right * cObj);
+				if (costs < min_costs) { min_costs = costs; best_pos = i; best_axis = axis; }
+				const size_t t = ids[b + i];
+				left.grow(&tlo[3 * t], &thi[3 * t]);
+				++count_left;
+				--count_right;
+			}
+		}
+		if (best_axis < 2) {
+			const float *cen = centroid.data();
+			const size_t axis = best_axis;
+			std::sort(first, last, [cen, axis](size_t i, size_t j) { return cen[3 * i + axis] > cen[3 * j + axis]; });
+		}
+		return best_pos;
+	}
+
 	/* Build the subtree over ids[b, b+n) into node slots [node, node+2n-1);
 	 * its leaves are leaf-order positions [b, b+n). */
 	void build(size_t b, size_t n, size_t node, bool may_spawn)
@@ -260,7 +324,7 @@ struct Builder {
 					break;
 				}
 				Box bb;
-				const size_t nl = split(t.b, t.n, bb);
+				const size_t nl = sah ? split_sah(t.b, t.n, bb) : split(t.b, t.n, bb);
 				put_box(t.node, bb);
 				s.nodes[t.node] = (uint32_t)(2 * t.n - 1);
 				const Task right{ t.b + nl, t.n - nl, t.node + 2 * nl };
@@ -315,7 +379,7 @@ struct Builder {
 };
 
 int finish(rtx_scene_impl *s, const std::vector<float> &verts3, size_t nverts, const uint32_t *faces, size_t nfaces,
-           int nthreads, rtx_scene **out)
+           int nthreads, rtx_scene **out, int method = RTX_SCENE_BVH_LONGEST_AXIS)
 {
 	s->vertices.resize(nverts);
 	for (size_t i = 0; i < nverts; ++i) s->vertices[i] = V4{ verts3[3 * i], verts3[3 * i + 1], verts3[3 * i + 2], 0 };
@@ -331,6 +395,7 @@ int finish(rtx_scene_impl *s, const std::vector<float> &verts3, size_t nverts, c
 	if (s->orig_faces.empty()) { delete s; return fail(RTX_SCENE_ERR_EMPTY, "mesh has no usable triangle"); }
 	vertex_normals(*s);
 	Builder bld(*s);
+	bld.sah = method == RTX_SCENE_BVH_SAH;
 	bld.prepare();
 	bld.run(nthreads);
 	const size_t nt = s->triangles.size();
@@ -351,25 +416,38 @@ inline const rtx_scene_impl *impl(const rtx_scene *s) { return reinterpret_cast<
 
 extern "C" {
 
-int rtx_scene_from_off(const char *path, int nthreads, rtx_scene **out)
+int rtx_scene_from_off_method(const char *path, int method, int nthreads, rtx_scene **out)
 {
 	if (!out) return fail(RTX_SCENE_ERR_ARG, "null output pointer");
 	*out = nullptr;
+	if (method != RTX_SCENE_BVH_LONGEST_AXIS && method != RTX_SCENE_BVH_SAH) return fail(RTX_SCENE_ERR_ARG, "unknown BVH method");
 	std::vector<float> verts3;
 	std::vector<uint32_t> faces;
 	size_t nverts = 0;
 	const int rc = read_off(path, verts3, faces, nverts);
 	if (rc != RTX_SCENE_OK) return rc;
-	return finish(new rtx_scene_impl, verts3, nverts, faces.data(), faces.size() / 3, nthreads, out);
+	return finish(new rtx_scene_impl, verts3, nverts, faces.data(), faces.size() / 3, nthreads, out, method);
+}
+
+int rtx_scene_from_mesh_method(const float *verts3, size_t nverts, const uint32_t *faces, size_t nfaces, int method, int nthreads,
+                               rtx_scene **out)
+{
+	if (!out) return fail(RTX_SCENE_ERR_ARG, "null output pointer");
+	*out = nullptr;
+	if (method != RTX_SCENE_BVH_LONGEST_AXIS && method != RTX_SCENE_BVH_SAH) return fail(RTX_SCENE_ERR_ARG, "unknown BVH method");
+	if (!verts3 || !faces || nverts == 0 || nfaces == 0) return fail(RTX_SCENE_ERR_ARG, "empty mesh");
+	std::vector<float> v(verts3, verts3 + 3 * nverts);
+	return finish(new rtx_scene_impl, v, nverts, faces, nfaces, nthreads, out, method);
+}
+
+int rtx_scene_from_off(const char *path, int nthreads, rtx_scene **out)
+{
+	return rtx_scene_from_off_method(path, RTX_SCENE_BVH_LONGEST_AXIS, nthreads, out);
 }
 
 int rtx_scene_from_mesh(const float *verts3, size_t nverts, const uint32_t *faces, size_t nfaces, int nthreads, rtx_scene **out)
 {
-	if (!out) return fail(RTX_SCENE_ERR_ARG, "null output pointer");
-	*out = nullptr;
-	if (!verts3 || !faces || nverts == 0 || nfaces == 0) return fail(RTX_SCENE_ERR_ARG, "empty mesh");
-	std::vector<float> v(verts3, verts3 + 3 * nverts);
-	return finish(new rtx_scene_impl, v, nverts, faces, nfaces, nthreads, out);
+	return rtx_scene_from_mesh_method(verts3, nverts, faces, nfaces, RTX_SCENE_BVH_LONGEST_AXIS, nthreads, out);
 }
 
 void rtx_scene_free(rtx_scene *scene) { delete reinterpret_cast<rtx_scene_impl *>(scene); }

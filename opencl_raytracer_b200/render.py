@@ -27,8 +27,9 @@ def parse(argv):
     ap.add_argument("-m", "--ambient-occlusion-method", choices=["uniform", "random"], default="uniform")
     ap.add_argument("-f", "--focal-length", type=float, default=1.0)
     ap.add_argument("-s", "--supersamples", type=int, default=4)
-    ap.add_argument("-r", "--bvh-strategy", choices=["longest"], default="longest",
-                    help="the O(n^2) SAH builder of bvh.cc:178-236 is not rebuilt here")
+    ap.add_argument("-r", "--bvh-strategy", choices=["longest", "sah"], default="longest",
+                    help="render.cc:30: cut along the longest axis (default) or the surface-area heuristic of bvh.cc:178-236 "
+                         "(same tree as the reference's O(n^2) builder, built in O(n log^2 n))")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--device-build", action="store_true", help="build normals and BVH on the device (rtx_upload_mesh)")
     ap.add_argument("--scene-cache", metavar="DIR", default=None,
@@ -43,7 +44,8 @@ def main(argv=None) -> int:
                        aoNumSamples=a.ambient_occlusion_samples, aoMethod=0 if a.ambient_occlusion_method == "uniform" else 1,
                        aoAlphaMin=4, aoAlphaMax=90)
     t0 = time.perf_counter()
-    sc = scene.cached_scene_from_off(a.input_mesh, a.scene_cache) if a.scene_cache else scene.scene_from_off(a.input_mesh)
+    sah = a.bvh_strategy == "sah"
+    sc = scene.cached_scene_from_off(a.input_mesh, a.scene_cache, sah=sah) if a.scene_cache else scene.scene_from_off(a.input_mesh, sah=sah)
     t1 = time.perf_counter()
     rt = host.RayTracer(opt)
     with host.CudaHost(rt, device=a.device) as h:

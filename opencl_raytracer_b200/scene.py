@@ -37,6 +37,10 @@ def _load():
         lib.rtx_scene_from_off.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         lib.rtx_scene_from_mesh.restype = C.c_int
         lib.rtx_scene_from_mesh.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+        lib.rtx_scene_from_off_method.restype = C.c_int
+        lib.rtx_scene_from_off_method.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        lib.rtx_scene_from_mesh_method.restype = C.c_int
+        lib.rtx_scene_from_mesh_method.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         lib.rtx_scene_free.restype = None
         lib.rtx_scene_free.argtypes = [C.c_void_p]
         lib.rtx_scene_counts.restype = None
@@ -108,22 +112,22 @@ def _wrap(lib, handle, name: str) -> Scene:
         lib.rtx_scene_free(handle)
 
 
-def scene_from_off(path: str, nthreads: int = 0) -> Scene:
-    """load_off_mesh + compute_vertex_normals + BVH::buildBVH + face sort."""
+def scene_from_off(path: str, nthreads: int = 0, sah: bool = False) -> Scene:
+    """load_off_mesh + compute_vertex_normals + BVH::buildBVH + face sort.  sah: the reference's `-r sah` builder."""
     lib = _load()
     h = C.c_void_p()
-    rc = lib.rtx_scene_from_off(os.fsencode(path), nthreads, C.byref(h))
+    rc = lib.rtx_scene_from_off_method(os.fsencode(path), 1 if sah else 0, nthreads, C.byref(h))
     if rc != 0:
         raise SceneError(rc, lib.rtx_scene_last_error().decode())
     return _wrap(lib, h, os.path.basename(path))
 
 
-def scene_from_mesh(verts3, faces, nthreads: int = 0, name: str = "") -> Scene:
+def scene_from_mesh(verts3, faces, nthreads: int = 0, name: str = "", sah: bool = False) -> Scene:
     lib = _load()
     verts3 = np.ascontiguousarray(verts3, np.float32).reshape(-1, 3)
     faces = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
     h = C.c_void_p()
-    rc = lib.rtx_scene_from_mesh(verts3.ctypes.data, verts3.shape[0], faces.ctypes.data, faces.shape[0], nthreads, C.byref(h))
+    rc = lib.rtx_scene_from_mesh_method(verts3.ctypes.data, verts3.shape[0], faces.ctypes.data, faces.shape[0], 1 if sah else 0, nthreads, C.byref(h))
     if rc != 0:
         raise SceneError(rc, lib.rtx_scene_last_error().decode())
     return _wrap(lib, h, name)
@@ -185,11 +189,11 @@ def mesh_key(verts3, faces) -> str:
     return h.hexdigest()[:32]
 
 
-def cached_scene_from_mesh(verts3, faces, cache_dir: str, nthreads: int = 0, name: str = "") -> Scene:
+def cached_scene_from_mesh(verts3, faces, cache_dir: str, nthreads: int = 0, name: str = "", sah: bool = False) -> Scene:
     """scene_from_mesh through an on-disk cache: the 10 M-triangle scene of C4 loads in a fraction of its 2 s build.
     A missing, unreadable or corrupt entry is rebuilt and rewritten."""
     os.makedirs(cache_dir, exist_ok=True)
-    path = os.path.join(cache_dir, "scene_%s.npz" % mesh_key(verts3, faces))
+    path = os.path.join(cache_dir, "scene_%s%s.npz" % (mesh_key(verts3, faces), "_sah" if sah else ""))
     if os.path.exists(path):
         try:
             sc = load_scene(path)
@@ -197,15 +201,15 @@ def cached_scene_from_mesh(verts3, faces, cache_dir: str, nthreads: int = 0, nam
             return sc
         except SceneError:
             pass
-    sc = scene_from_mesh(verts3, faces, nthreads=nthreads, name=name)
+    sc = scene_from_mesh(verts3, faces, nthreads=nthreads, name=name, sah=sah)
     save_scene(path, sc)
     return sc
 
 
-def cached_scene_from_off(path: str, cache_dir: str, nthreads: int = 0) -> Scene:
-    """scene_from_off through the same cache, keyed by the sha256 of the OFF file's bytes."""
+def cached_scene_from_off(path: str, cache_dir: str, nthreads: int = 0, sah: bool = False) -> Scene:
+    """scene_from_off through the same cache, keyed by the sha256 of the OFF file's bytes (and the builder)."""
     os.makedirs(cache_dir, exist_ok=True)
-    h = hashlib.sha256(b"rtx-scene-off-%d" % CACHE_FORMAT)
+    h = hashlib.sha256(b"rtx-scene-off-%d-%d" % (CACHE_FORMAT, 1 if sah else 0))
     with open(path, "rb") as fh:
         for chunk in iter(lambda: fh.read(1 << 20), b""):
             h.update(chunk)
@@ -215,6 +219,6 @@ def cached_scene_from_off(path: str, cache_dir: str, nthreads: int = 0) -> Scene
             return load_scene(entry)
         except SceneError:
             pass
-    sc = scene_from_off(path, nthreads=nthreads)
+    sc = scene_from_off(path, nthreads=nthreads, sah=sah)
     save_scene(entry, sc)
     return sc

@@ -88,6 +88,25 @@ def test_python_cli_mirror_writes_the_same_pgm(tmp_path, scene_mod, soup_golden,
         assert np.array_equal(read_pgm(pgm), want), extra
 
 
+@pytest.mark.gpu
+def test_python_cli_mirror_sah_strategy(tmp_path, scene_mod, sah_golden):
+    """`-r sah`: the reference's own parser crashes on the option (see above); the mirror builds the reference's SAH tree
+    on the host (rtx_scene_from_off_method) and must write the PGM the reference kernel text renders from that tree."""
+    require_gpu()
+    import sys
+    from opencl_raytracer_b200 import scenes
+    g = sah_golden
+    v, f = scenes.random_soup(300, seed=11)
+    off, pgm = str(tmp_path / "soup.off"), str(tmp_path / "out.pgm")
+    scene_mod.write_off(off, v, f)
+    cmd = [sys.executable, "-m", "opencl_raytracer_b200.render", "-a", "0", "-r", "sah", "-w", str(int(g["width"])), "-h", str(int(g["height"])),
+           "-s", str(int(g["nss"])), "--scene-cache", str(tmp_path / "cache"), off, pgm]
+    for _ in range(2):                                   # second run: the tree comes from the on-disk cache
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert np.array_equal(read_pgm(pgm), g["u8"])
+
+
 def test_reference_cli_fails_loudly_without_a_device(tmp_path, scene_mod, soup_golden):
     from opencl_raytracer_b200 import host
     if host.device_count() > 0:

@@ -152,3 +152,40 @@ def test_scene_cache_keyed_by_off_file(tmp_path):
     b = scn.cached_scene_from_off(off, str(tmp_path / "c"))
     assert a.digest() == b.digest() == scn.scene_from_off(off).digest()
     assert len(list((tmp_path / "c").glob("*.npz"))) == 1
+
+
+def test_sah_builder_emits_the_reference_tree(sah_golden):
+    """BVH::Method::SURFACE_AREA_HEURISTIC (bvh.cc:178-236, `-r sah`) on the host: the golden arrays come from the
+    reference's own builder (tests/golden/make_golden.py sah)."""
+    from opencl_raytracer_b200 import scene as scn, scenes
+    v, f = scenes.random_soup(300, seed=11)
+    sc = scn.scene_from_mesh(v, f, sah=True)
+    g = sah_golden
+    for key, got in (("t_faces", sc.faces), ("t_nodes", sc.nodes), ("t_aabbs", sc.aabbs), ("t_vertices", sc.vertices), ("t_normals", sc.normals)):
+        assert np.array_equal(g[key], got), key
+    assert not np.array_equal(scn.scene_from_mesh(v, f).nodes, sc.nodes)        # another topology than the default builder
+    assert sc.digest() == scn.scene_from_mesh(v, f, sah=True, nthreads=1).digest()
+
+
+def test_sah_builder_against_the_reference_builder_with_ties(po):
+    """Regular grids give many equal centroids: the order std::sort leaves them in decides the tree.  Runs where the
+    reference's bvh.cc was compiled (oracle/_ref); the reference prints one line per cut candidate, so stdout is muted."""
+    import sys
+    from opencl_raytracer_b200 import scene as scn, scenes
+    try:
+        po.ref()
+    except Exception as e:
+        pytest.skip("oracle/_ref not built: %s" % e)
+    for v, f in (scenes.sibenik_standin(detail=0.06), scenes.random_soup(120, seed=9)):
+        sys.stdout.flush()
+        saved, devnull = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        try:
+            r = po.ref_scene_from_mesh(v, f, sah=True)
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull)
+            os.close(saved)
+        m = scn.scene_from_mesh(v, f, sah=True)
+        for a, b in ((r.faces, m.faces), (r.nodes, m.nodes), (r.aabbs, m.aabbs), (r.triangles, m.triangles)):
+            assert np.array_equal(a, b)
