@@ -838,6 +838,30 @@ def main():
                 hx.upload_scene(sc)
                 ms = kernel_ms(hx)
                 extras[name] = {"kernel_ms": ms, "Mrays/s": rays / ms / 1e3}
+        # the same frame on the reference's OTHER tree (`-r sah`, bvh.cc:178-236; built by the host builder of this repo, which
+        # emits the reference builder's arrays): kernel time + sampled rows against the oracle walking that tree
+        try:
+            from oracle import pyoracle as po
+            from opencl_raytracer_b200 import scene as scene_mod
+            t0 = time.perf_counter()
+            sc_sah = scene_mod.scene_from_mesh(sc.vertices[:, :3], sc.orig_faces.reshape(-1, 3), sah=True)
+            build_s = time.perf_counter() - t0
+            with host.CudaHost(rt, device=local_rank) as hx:
+                hx.upload_scene(sc_sah)
+                ms = kernel_ms(hx)
+                got = hx.download()
+            rows = list(range(th // 16, th, th // 8))
+            bad = 0
+            for y in rows:
+                want = po.render(sc_sah, tw, th, 1.0, True, rows=(y, y + 1, 1), want_ids=False).image
+                bad += int((got[y] != want[y]).sum())
+            extras["sah_tree"] = {"kernel_ms": ms, "Mrays/s": rays / ms / 1e3, "host_build_s": build_s,
+                                  "parity": {"rows_vs_oracle": len(rows), "pixels_differing": bad},
+                                  "what": "the reference's `-r sah` tree of the same mesh (scene_prep.cc::split_sah: the reference builder's arrays, "
+                                          "O(n log n) per node instead of O(n^2))"}
+            del got
+        except Exception as e:                                              # an extra must not cost the headline line
+            extras["sah_tree"] = {"unavailable": str(e)}
         with host.CudaHost(rt, device=local_rank) as hx:                  # the tree itself built on the device
             hx.upload_mesh(sc.vertices, sc.orig_faces, sc.normals)
             t0 = time.perf_counter()
